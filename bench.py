@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native FiDiBench hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Metric (BASELINE.json): GCUPS = FP64 cell-updates per second of the 3-D first-order
+upwind step (ref: upwind/cxx/upwind.cxx:51-86), whole job over all N GPUs.
+One bench "step" = one Upwind::advect(numTimeSteps=T) call (T = 100, BASELINE
+config 2) over the resident field.  N = 1 runs 512^3 (configs[1]); N > 1 keeps
+512^3 cells per GPU (weak scaling), slabs along axis 0 with an NCCL halo ring:
+N=2 -> 1024x512x512, N=4 -> 1024x1024x512, N=8 -> 1024^3 (configs[2]).
+`--workload upwind1024` runs 1024^3 on every N instead (strong scaling).
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom of main()).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_UPDATE = 16.0  # one FP64 read + one FP64 write per cell-update
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload_dims(workload: str, n: int):
+    if workload == "upwind512":      # weak: 512^3 cells per GPU
+        dims = {1: (512, 512, 512), 2: (1024, 512, 512), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}.get(n)
+        if dims is None:
+            dims = (512 * n, 512, 512)
+        return dims, "weak"
+    if workload == "upwind1024":     # strong: BASELINE configs[2]
+        return (1024, 1024, 1024), "strong"
+    if workload == "upwind128":      # configs[0], parity-sized (launch-bound)
+        return (128, 128, 128), "strong"
+    if workload == "upwind2048":     # configs[4], 8 GPUs
+        return (2048, 2048, 2048), "strong"
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy read+write)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thread, self.gpu = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            p = [x.strip() for x in row.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref = the untouched
+    upwind.cxx compiled with OpenMP; else the oracle port), all host threads, on a
+    bounded sample of the same workload."""
+    if rank != 0:
+        return 0
+    import numpy as np
+    import oracle
+    dims, scaling = workload_dims(args.workload, args.gpus)
+    ncpu = os.cpu_count() or 1
+    # bounded sample: the same 512^3-cells-per-GPU grid is far too slow on the host at
+    # 100 time steps; keep the single-GPU grid (the reference's own published case is
+    # 512^3 x 10, pictures/mahuika.py:13) and calibrate the time steps per bench step
+    sdims = (512, 512, 512) if dims[0] >= 512 else dims
+    cells = float(np.prod(sdims))
+    use_ref = oracle.ref_available()
+    if use_ref:
+        r = oracle.ref()
+        r.set_threads(ncpu)
+        threads = r.threads()
+        run = lambda t: r.upwind_run(sdims, t, want_field=False)["seconds"]
+        kind = "reference"
+    else:
+        threads = oracle.c.num_threads()
+        f0 = np.zeros(sdims); f0.reshape(-1)[0] = 1.0
+        def run(t):
+            t0 = time.perf_counter(); oracle.c.upwind_advect(f0, t); return time.perf_counter() - t0
+        kind = "port"
+    t1 = run(1)  # calibration (also first-touch)
+    budget = 150.0
+    tsteps = int(max(1, min(args.tsteps, budget / max(t1, 1e-3) / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        run(tsteps)
+    secs = 0.0
+    for _ in range(args.steps):
+        secs += run(tsteps)
+    value = cells * tsteps * args.steps / secs / 1e9
+    sample = f"{sdims[0]}x{sdims[1]}x{sdims[2]} grid, {tsteps} time step(s) per bench step, advect() only"
+    line = {
+        "impl": "reference", "metric": "GCUPS (FP64 cell-updates/s), upwind 3-D", "value": value, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"upwind3d {dims[0]}x{dims[1]}x{dims[2]} x{args.tsteps} time steps (reference arm: "
+                               f"bounded sample {sample})", "parallelism": f"openmp{threads}"},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline(sdims, tsteps_hint=10):
+    """oracle/_ref (the untouched reference, OpenMP on every host core) timed on a bounded
+    sample; reported beside the GPU number, not a target."""
+    import numpy as np
+    import oracle
+    ncpu = os.cpu_count() or 1
+    cells = float(np.prod(sdims))
+    if oracle.ref_available():
+        r = oracle.ref()
+        r.set_threads(ncpu)
+        threads, kind = r.threads(), "reference"
+        run = lambda t: r.upwind_run(sdims, t, want_field=False)["seconds"]
+    else:
+        threads, kind = oracle.c.num_threads(), "port"
+        f0 = np.zeros(sdims); f0.reshape(-1)[0] = 1.0
+        def run(t):
+            t0 = time.perf_counter(); oracle.c.upwind_advect(f0, t); return time.perf_counter() - t0
+    t1 = run(1)
+    tsteps = int(max(1, min(tsteps_hint, 15.0 / max(t1, 1e-3))))
+    secs = run(tsteps)
+    return {"value": cells * tsteps / secs / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
+            "sample": f"{sdims[0]}x{sdims[1]}x{sdims[2]} x {tsteps} time steps, advect() only, "
+                      f"{'untouched upwind.cxx -O3 -fopenmp' if kind == 'reference' else 'oracle/fdb_oracle.c'}"}
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="upwind512")
+    ap.add_argument("--tsteps", type=int, default=100, help="time steps per advect() call (= per bench step)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tma"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fidibench_b200 as fb
+
+    if not torch.cuda.is_available() or fb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = fb.Comm.from_torch_distributed(device=local_rank)
+
+    dims, scaling = workload_dims(args.workload, world)
+    base = float(min(dims))
+    lengths = [d / base for d in dims]        # same resolution in each direction, as the reference's main()
+    T = args.tsteps
+    up = fb.Upwind([1.0, 1.0, 1.0], lengths, dims, comm=comm)
+    if args.kernel != "auto":
+        up.set_kernel(fb.FDB_KERNEL_GENERIC if args.kernel == "generic" else fb.FDB_KERNEL_TMA)
+    kernel_name = "upwind3d_tma_kernel" if up.kernel() == fb.FDB_KERNEL_TMA else "upwind_generic_kernel"
+    dt = up.default_dt()
+    slab_cells = up.slab_cells()
+    total_cells = float(np.prod(dims))
+
+    # synthetic input: uniform random FP64 field in pinned host memory (one slab per rank)
+    gen = torch.Generator().manual_seed(20261017 + rank)
+    host = torch.empty(slab_cells, dtype=torch.float64, pin_memory=True)
+    host.uniform_(0.0, 1.0, generator=gen)
+    host_np = host.numpy()
+    up.set_slab(host_np)
+
+    stream = torch.cuda.Stream()
+    up.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ------------------------------------------
+    for _ in range(args.warmup):
+        up.advect_async(T, dt)
+    up.sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = fb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        up.advect_async(T, dt)
+    e1.record(stream)
+    up.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = fb.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    secs = ms / 1e3
+    value = total_cells * T * args.steps / secs / 1e9
+    halo = up.last_timing()["halo_bytes"]
+
+    # ---- end to end through the public API with HOST buffers ("e2e") ---------------------
+    e2e = None
+    if not args.no_e2e:
+        up.set_stream(None)
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            up.set_slab(host_np); up.advect(T, dt); up.checksum()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            up.set_slab(host_np)      # host -> device copy of this step's field (pinned)
+            up.advect(T, dt)
+            chk = up.checksum()       # device -> host read of the step's result
+        torch.cuda.synchronize()
+        t1 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t1], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t1 = float(t.item())
+        e2e = {"value": total_cells * T * e2e_steps / t1 / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": int(slab_cells * 8), "d2h_bytes_per_step": int(dims[0] * 8),
+               "steps": e2e_steps, "checksum": chk,
+               "what": "fdb_upwind_set_slab(pinned host) + fdb_upwind_advect(T) + fdb_upwind_checksum per step"}
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peak, peak_src = measured_peak()
+    n_kernel_launches = T * args.steps            # one sweep kernel per time step (interior) per rank
+    avg_launch_ms = ms / n_kernel_launches
+    algo_bytes_per_launch = slab_cells * ALGO_BYTES_PER_UPDATE
+    achieved = algo_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
+        key = f"{kernel_name}:{dims[0] // world}x{dims[1]}x{dims[2]}"
+        traffic = tj.get(key)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+                "how": "16 B per cell-update x cells of one launch / (CUDA-event time of the timed region / launches)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline((512, 512, 512) if dims[0] >= 512 else dims)
+
+    if rank == 0:
+        line = {
+            "metric": "GCUPS (FP64 cell-updates/s), upwind 3-D", "value": value, "unit": "GCUPS",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (uniform random FP64 field)",
+            "config": {"workload": f"upwind3d {dims[0]}x{dims[1]}x{dims[2]} x{T} time steps per step",
+                       "cells_per_gpu": int(slab_cells), "parallelism": f"slab{world}" if world > 1 else "single",
+                       "kernel": kernel_name,
+                       "l2": "inputs larger than L2 (2 ping-pong fields of %.2f GiB per GPU)" % (slab_cells * 8 / 2**30)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "halo_bytes_per_gpu": halo,
+        }
+        print(json.dumps(line), flush=True)
+    up.close()
+    if comm is not None:
+        comm.close()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

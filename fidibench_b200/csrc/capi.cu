@@ -1,0 +1,726 @@
+// capi.cu -- the extern "C" surface declared in include/fidib200.h.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "fdb_internal.h"
+
+using namespace fdb;
+
+// ---- handles ----------------------------------------------------------------------
+struct fdb_upwind {
+  Field field;
+  double velocity[3] = {0, 0, 0};  // reference axis order
+  double lengths[3] = {1, 1, 1};
+  int64_t num_cells[3] = {1, 1, 1};
+  int kernel = FDB_KERNEL_AUTO;
+  int fuse = 1;
+};
+
+struct fdb_stencil {
+  Field field;
+  StencilBranches br;
+  int ndims = 3;
+  int64_t dims[3] = {1, 1, 1};
+  bool out_valid = false;  // buf[1-cur] holds the last apply's output
+  int kernel = FDB_KERNEL_AUTO;
+};
+
+namespace {
+
+struct UpwindSweep : SweepLauncher {
+  UpwindCoeffs k;
+  bool tma = false;
+  int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    return tma ? launch_upwind_tma(*f, d, ibeg, iend, k, s)
+               : launch_upwind_generic(*f, d, ibeg, iend, k, s);
+  }
+};
+
+struct StencilSweep : SweepLauncher {
+  const StencilBranches* b = nullptr;
+  bool fast = false;
+  int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    return fast ? launch_stencil_lap7(*f, d, ibeg, iend, *b, s)
+                : launch_stencil_generic(*f, d, ibeg, iend, *b, s);
+  }
+};
+
+// ref: upwind.cxx:34-36,72 -- upDirection, deltas and the per-axis coefficient
+// ((deltaTime * v[j]) * upDirection[j]) / deltas[j], evaluated left to right.
+void upwind_coeffs(const fdb_upwind* h, double dt, UpwindCoeffs* k) {
+  const Geometry& g = h->field.geo;
+  for (int a = 0; a < 3; ++a) { k->c[a] = 0.0; k->up[a] = -1; k->active[a] = false; }
+  for (int j = 0; j < g.ndims; ++j) {
+    const int a = g.axis_of[j];
+    const int up = (h->velocity[j] < 0.) ? +1 : -1;
+    const double delta = h->lengths[j] / (double)(size_t)h->num_cells[j];
+    k->c[a] = dt * h->velocity[j] * up / delta;
+    k->up[a] = up;
+    k->active[a] = true;
+  }
+}
+
+int timing_begin(Field* f) {
+  f->last_halo_bytes = 0;
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_CUDA(cudaEventRecord(s.ev_t0, s.s_main));
+  }
+  return FDB_OK;
+}
+int timing_end(Field* f) {
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_CUDA(cudaEventRecord(s.ev_t1, s.s_main));
+  }
+  return FDB_OK;
+}
+int timing_collect(Field* f) {
+  double ms = 0;
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_CUDA(cudaEventSynchronize(s.ev_t1));
+    float t = 0;
+    if (cudaEventElapsedTime(&t, s.ev_t0, s.ev_t1) == cudaSuccess) ms = std::max(ms, (double)t);
+    (void)cudaGetLastError();
+  }
+  f->last_ms = ms;
+  return FDB_OK;
+}
+
+int upwind_common_create(int ndims, const int64_t* numCells, const double* velocity,
+                         const double* lengths, int ngpus, fdb_comm* comm, fdb_upwind** out) {
+  if (!out) return set_error(FDB_E_INVALID, "null output handle");
+  *out = nullptr;
+  if (!numCells || !velocity || !lengths) return set_error(FDB_E_INVALID, "null argument");
+  Geometry geo;
+  FDB_TRY(make_geometry(ndims, numCells, &geo));
+  for (int j = 0; j < ndims; ++j)
+    if (!(lengths[j] > 0.0)) return set_error(FDB_E_INVALID, "lengths[%d] must be positive", j);
+  fdb_upwind* h = new (std::nothrow) fdb_upwind();
+  if (!h) return set_error(FDB_E_OOM, "out of host memory");
+  bool need_lo = false, need_hi = false;
+  for (int j = 0; j < ndims; ++j) {
+    h->velocity[j] = velocity[j];
+    h->lengths[j] = lengths[j];
+    h->num_cells[j] = numCells[j];
+    if (geo.axis_of[j] == 0 && geo.n[0] > 1) {
+      if (velocity[j] < 0.) need_hi = true; else need_lo = true;
+    }
+  }
+  int rc = field_create(&h->field, geo, 1, need_lo, need_hi, ngpus, comm, /*want_tma=*/true);
+  if (rc == FDB_OK) rc = field_fill_delta(&h->field, 0);
+  if (rc == FDB_OK) rc = field_sync(&h->field);
+  if (rc != FDB_OK) {
+    field_destroy(&h->field);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return FDB_OK;
+}
+
+// std::map<std::vector<int>, double> order (Filter.cpp:202)
+bool lex_less(const int* a, const int* b, int nd) {
+  for (int j = 0; j < nd; ++j) {
+    if (a[j] < b[j]) return true;
+    if (a[j] > b[j]) return false;
+  }
+  return false;
+}
+
+int stencil_common_create(int ndims, const int64_t* dims, int nbranch, const int* offsets,
+                          const double* weights, int ngpus, fdb_comm* comm, fdb_stencil** out) {
+  if (!out) return set_error(FDB_E_INVALID, "null output handle");
+  *out = nullptr;
+  if (!dims || !offsets || !weights) return set_error(FDB_E_INVALID, "null argument");
+  if (nbranch < 1 || nbranch > 32)
+    return set_error(FDB_E_INVALID, "nbranch must be in 1..32 (got %d)", nbranch);
+  Geometry geo;
+  FDB_TRY(make_geometry(ndims, dims, &geo));
+  fdb_stencil* h = new (std::nothrow) fdb_stencil();
+  if (!h) return set_error(FDB_E_OOM, "out of host memory");
+  h->ndims = ndims;
+  for (int j = 0; j < ndims; ++j) h->dims[j] = dims[j];
+  // sort the branches the way std::map iterates them
+  std::vector<int> order(nbranch);
+  for (int b = 0; b < nbranch; ++b) order[b] = b;
+  std::sort(order.begin(), order.end(), [&](int x, int y) {
+    return lex_less(offsets + x * ndims, offsets + y * ndims, ndims);
+  });
+  for (int b = 1; b < nbranch; ++b)
+    if (!lex_less(offsets + order[b - 1] * ndims, offsets + order[b] * ndims, ndims)) {
+      delete h;
+      return set_error(FDB_E_INVALID, "duplicate stencil offset (a std::map key can appear once)");
+    }
+  int G = 0;
+  bool need_lo = false, need_hi = false;
+  h->br.nbranch = nbranch;
+  for (int b = 0; b < nbranch; ++b) {
+    const int* o = offsets + order[b] * ndims;
+    int io[3] = {0, 0, 0};
+    for (int j = 0; j < ndims; ++j) io[geo.axis_of[j]] = o[j];
+    for (int a = 0; a < 3; ++a) h->br.off[b][a] = io[a];
+    h->br.w[b] = weights[order[b]];
+    if (geo.n[0] > 1) {
+      if (io[0] < 0) need_lo = true;
+      if (io[0] > 0) need_hi = true;
+      G = std::max(G, std::abs(io[0]));
+    } else {
+      h->br.off[b][0] = 0;  // a single plane is its own periodic neighbour
+    }
+  }
+  if (G == 0) G = 1;
+  int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/true);
+  if (rc == FDB_OK) rc = field_sync(&h->field);
+  if (rc != FDB_OK) {
+    field_destroy(&h->field);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return FDB_OK;
+}
+
+}  // namespace
+
+#define FDB_GUARD_BEGIN try {
+#define FDB_GUARD_END                                                    \
+  }                                                                      \
+  catch (const std::bad_alloc&) {                                        \
+    return set_error(FDB_E_OOM, "out of host memory");                   \
+  }                                                                      \
+  catch (...) {                                                          \
+    return set_error(FDB_E_INVALID, "unexpected C++ exception");         \
+  }
+
+extern "C" {
+
+const char* fdb_last_error(void) { return last_error(); }
+
+int fdb_version(int* major, int* minor) {
+  if (major) *major = FDB_VERSION_MAJOR;
+  if (minor) *minor = FDB_VERSION_MINOR;
+  return FDB_OK;
+}
+
+int fdb_device_count(int* count) {
+  if (!count) return set_error(FDB_E_INVALID, "null argument");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    (void)cudaGetLastError();
+    return set_error(FDB_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return FDB_OK;
+}
+
+int fdb_launch_count(int64_t* count) {
+  if (!count) return set_error(FDB_E_INVALID, "null argument");
+  *count = launch_count();
+  return FDB_OK;
+}
+
+int fdb_slab_partition(int64_t n0, int nparts, int part, int64_t* lo, int64_t* hi) {
+  if (!lo || !hi || n0 < 1 || nparts < 1 || part < 0 || part >= nparts)
+    return set_error(FDB_E_INVALID, "bad slab partition request (n0=%lld nparts=%d part=%d)",
+                     (long long)n0, nparts, part);
+  if (n0 % nparts != 0)
+    return set_error(FDB_E_DECOMP,
+                     "No valid domain decomposition: %d slab(s) do not divide the %lld planes of axis 0",
+                     nparts, (long long)n0);
+  const int64_t nloc = n0 / nparts;
+  *lo = part * nloc;
+  *hi = *lo + nloc;
+  return FDB_OK;
+}
+
+// ---- communicator ---------------------------------------------------------------------
+int fdb_comm_unique_id(void* id_bytes) {
+  if (!id_bytes) return set_error(FDB_E_INVALID, "null argument");
+  static_assert(sizeof(ncclUniqueId) <= FDB_COMM_ID_BYTES, "id size");
+  ncclUniqueId id;
+  FDB_NCCL(ncclGetUniqueId(&id));
+  memset(id_bytes, 0, FDB_COMM_ID_BYTES);
+  memcpy(id_bytes, &id, sizeof(id));
+  return FDB_OK;
+}
+
+int fdb_comm_create(int rank, int nranks, const void* id_bytes, int device, fdb_comm** out) {
+  FDB_GUARD_BEGIN
+  if (!out) return set_error(FDB_E_INVALID, "null output handle");
+  *out = nullptr;
+  if (nranks < 1 || rank < 0 || rank >= nranks || (!id_bytes && nranks > 1))
+    return set_error(FDB_E_INVALID, "bad communicator request (rank=%d nranks=%d)", rank, nranks);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return set_error(FDB_E_CUDA, "device %d not available (%d visible); no CPU fallback", device, ndev);
+  }
+  fdb_comm* c = new fdb_comm();
+  c->rank = rank;
+  c->nranks = nranks;
+  c->device = device;
+  FDB_CUDA(cudaSetDevice(device));
+  FDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  FDB_CUDA(cudaMalloc(&c->scratch, 64 * sizeof(double)));
+  c->scratch_doubles = 64;
+  if (nranks > 1) {
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    FDB_NCCL(ncclCommInitRank(&c->nccl, nranks, id, rank));
+  }
+  *out = c;
+  return FDB_OK;
+  FDB_GUARD_END
+}
+
+int fdb_comm_rank(const fdb_comm* c, int* rank, int* nranks) {
+  if (!c) return set_error(FDB_E_INVALID, "null communicator");
+  if (rank) *rank = c->rank;
+  if (nranks) *nranks = c->nranks;
+  return FDB_OK;
+}
+
+int fdb_comm_max(fdb_comm* c, double* value) {
+  if (!c || !value) return set_error(FDB_E_INVALID, "null argument");
+  if (c->nranks == 1) return FDB_OK;
+  FDB_CUDA(cudaSetDevice(c->device));
+  FDB_CUDA(cudaMemcpyAsync(c->scratch, value, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  FDB_NCCL(ncclAllReduce(c->scratch, c->scratch + 1, 1, ncclDouble, ncclMax, c->nccl, c->stream));
+  count_launch();
+  FDB_CUDA(cudaMemcpyAsync(value, c->scratch + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  FDB_CUDA(cudaStreamSynchronize(c->stream));
+  return FDB_OK;
+}
+
+int fdb_comm_barrier(fdb_comm* c) {
+  double v = 0.0;
+  return fdb_comm_max(c, &v);
+}
+
+int fdb_comm_destroy(fdb_comm* c) {
+  if (!c) return FDB_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->nccl) ncclCommDestroy(c->nccl);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  (void)cudaGetLastError();
+  delete c;
+  return FDB_OK;
+}
+
+// ---- upwind -----------------------------------------------------------------------------
+int fdb_upwind_create(int ndims, const int64_t* numCells, const double* velocity,
+                      const double* lengths, int ngpus, fdb_upwind** out) {
+  FDB_GUARD_BEGIN
+  return upwind_common_create(ndims, numCells, velocity, lengths, ngpus, nullptr, out);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_create_dist(int ndims, const int64_t* numCells, const double* velocity,
+                           const double* lengths, fdb_comm* comm, fdb_upwind** out) {
+  FDB_GUARD_BEGIN
+  if (!comm) return set_error(FDB_E_INVALID, "null communicator");
+  return upwind_common_create(ndims, numCells, velocity, lengths, 1, comm, out);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_local_range(const fdb_upwind* h, int64_t* lo, int64_t* hi) {
+  if (!h || !lo || !hi) return set_error(FDB_E_INVALID, "null argument");
+  *lo = h->field.slabs.front().lo;
+  *hi = h->field.slabs.back().hi;
+  return FDB_OK;
+}
+
+int fdb_upwind_set_field(fdb_upwind* h, const double* host_field) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_field) return set_error(FDB_E_INVALID, "null argument");
+  FDB_TRY(field_upload(&h->field, h->field.cur, host_field, nullptr));
+  return field_sync(&h->field);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_set_slab(fdb_upwind* h, const double* host_slab) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
+  FDB_TRY(field_upload(&h->field, h->field.cur, nullptr, host_slab));
+  return field_sync(&h->field);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_reset(fdb_upwind* h) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  FDB_TRY(field_fill_delta(&h->field, h->field.cur));
+  return field_sync(&h->field);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_default_dt(const fdb_upwind* h, double* dt) {
+  if (!h || !dt) return set_error(FDB_E_INVALID, "null argument");
+  // ref: upwind.cxx:186-192
+  const double courant = 0.1;
+  double best = DBL_MAX;
+  for (int j = 0; j < h->field.geo.ndims; ++j) {
+    const double dx = h->lengths[j] / (double)(size_t)h->num_cells[j];
+    const double val = courant * dx / h->velocity[j];
+    best = (val < best ? val : best);
+  }
+  *dt = best;
+  return FDB_OK;
+}
+
+int fdb_upwind_get_kernel(const fdb_upwind* h, int* kernel) {
+  if (!h || !kernel) return set_error(FDB_E_INVALID, "null argument");
+  UpwindCoeffs k;
+  upwind_coeffs(h, 1.0, &k);
+  const bool can = upwind_tma_supported(h->field, k);
+  *kernel = (h->kernel == FDB_KERNEL_GENERIC || !can) ? FDB_KERNEL_GENERIC : FDB_KERNEL_TMA;
+  return FDB_OK;
+}
+
+int fdb_upwind_set_kernel(fdb_upwind* h, int kernel) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (kernel != FDB_KERNEL_AUTO && kernel != FDB_KERNEL_GENERIC && kernel != FDB_KERNEL_TMA)
+    return set_error(FDB_E_INVALID, "unknown kernel id %d", kernel);
+  if (kernel == FDB_KERNEL_TMA) {
+    UpwindCoeffs k;
+    upwind_coeffs(h, 1.0, &k);
+    if (!upwind_tma_supported(h->field, k))
+      return set_error(FDB_E_INVALID,
+                       "the TMA kernel needs a 3-D grid, non-negative velocities and an even last extent");
+  }
+  h->kernel = kernel;
+  return FDB_OK;
+}
+
+int fdb_upwind_set_fuse(fdb_upwind* h, int steps_per_sweep) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (steps_per_sweep != 1)
+    return set_error(FDB_E_INVALID, "temporal blocking (fuse > 1) is not available in this build");
+  h->fuse = steps_per_sweep;
+  return FDB_OK;
+}
+
+int fdb_upwind_set_stream(fdb_upwind* h, void* cuda_stream) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  return field_set_stream(&h->field, cuda_stream);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTime) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (numTimeSteps < 0) return set_error(FDB_E_INVALID, "negative step count");
+  Field* f = &h->field;
+  UpwindSweep sw;
+  upwind_coeffs(h, deltaTime, &sw.k);
+  int kern = FDB_KERNEL_GENERIC;
+  FDB_TRY(fdb_upwind_get_kernel(h, &kern));
+  sw.tma = (kern == FDB_KERNEL_TMA);
+  FDB_TRY(timing_begin(f));
+  for (int64_t s = 0; s < numTimeSteps; ++s) {
+    FDB_TRY(field_sweep(f, &sw));
+    f->cur = 1 - f->cur;
+  }
+  FDB_TRY(timing_end(f));
+  f->last_updates = (double)numTimeSteps * (double)f->geo.total();
+  return FDB_OK;
+  FDB_GUARD_END
+}
+
+int fdb_upwind_sync(fdb_upwind* h) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  FDB_TRY(field_sync(&h->field));
+  return timing_collect(&h->field);
+}
+
+int fdb_upwind_advect(fdb_upwind* h, int64_t numTimeSteps, double deltaTime) {
+  FDB_TRY(fdb_upwind_advect_async(h, numTimeSteps, deltaTime));
+  return fdb_upwind_sync(h);
+}
+
+int fdb_upwind_checksum(fdb_upwind* h, double* sum) {
+  FDB_GUARD_BEGIN
+  if (!h || !sum) return set_error(FDB_E_INVALID, "null argument");
+  return field_sum(&h->field, h->field.cur, sum);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_std(fdb_upwind* h, double* stddev) {
+  FDB_GUARD_BEGIN
+  if (!h || !stddev) return set_error(FDB_E_INVALID, "null argument");
+  // ref: upwind.cxx:95-103
+  double sum = 0, sq = 0;
+  FDB_TRY(field_sum(&h->field, h->field.cur, &sum));
+  const double ntot = (double)(size_t)h->field.geo.total();
+  const double mean = sum / ntot;
+  FDB_TRY(field_sqdev(&h->field, h->field.cur, mean, &sq));
+  *stddev = sqrt(sq / ntot);
+  return FDB_OK;
+  FDB_GUARD_END
+}
+
+int fdb_upwind_get_field(fdb_upwind* h, double* host_field) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_field) return set_error(FDB_E_INVALID, "null argument");
+  return field_download(&h->field, h->field.cur, host_field, nullptr);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_get_slab(fdb_upwind* h, double* host_slab) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
+  return field_download(&h->field, h->field.cur, nullptr, host_slab);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_last_timing(const fdb_upwind* h, double* gpu_ms, double* cell_updates,
+                           double* halo_bytes) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (gpu_ms) *gpu_ms = h->field.last_ms;
+  if (cell_updates) *cell_updates = h->field.last_updates;
+  if (halo_bytes) *halo_bytes = h->field.last_halo_bytes / (double)h->field.ngpus;
+  return FDB_OK;
+}
+
+int fdb_upwind_destroy(fdb_upwind* h) {
+  if (!h) return FDB_OK;
+  field_destroy(&h->field);
+  delete h;
+  return FDB_OK;
+}
+
+// ---- stencil (Filter) -----------------------------------------------------------------------
+int fdb_stencil_create(int ndims, const int64_t* globalDims, int nbranch, const int* offsets,
+                       const double* weights, int ngpus, fdb_stencil** out) {
+  FDB_GUARD_BEGIN
+  return stencil_common_create(ndims, globalDims, nbranch, offsets, weights, ngpus, nullptr, out);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_create_dist(int ndims, const int64_t* globalDims, int nbranch, const int* offsets,
+                            const double* weights, fdb_comm* comm, fdb_stencil** out) {
+  FDB_GUARD_BEGIN
+  if (!comm) return set_error(FDB_E_INVALID, "null communicator");
+  return stencil_common_create(ndims, globalDims, nbranch, offsets, weights, 1, comm, out);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_local_range(const fdb_stencil* h, int64_t* lo, int64_t* hi) {
+  if (!h || !lo || !hi) return set_error(FDB_E_INVALID, "null argument");
+  *lo = h->field.slabs.front().lo;
+  *hi = h->field.slabs.back().hi;
+  return FDB_OK;
+}
+
+// Column-major (first reference axis fastest) host data of extents d[0..nd) is the
+// row-major array of the reversed extents: permute on the device.
+static int stencil_colmajor_io(fdb_stencil* h, int which_buf, double* host, bool upload) {
+  Field* f = &h->field;
+  if (f->nparts != 1)
+    return set_error(FDB_E_STATE, "column-major transfers need a single-device handle");
+  if (h->ndims == 1) {
+    return upload ? field_upload(f, which_buf, host, nullptr) : field_download(f, which_buf, host, nullptr);
+  }
+  Slab& s = f->slabs[0];
+  FDB_CUDA(cudaSetDevice(s.device));
+  const int64_t total = f->geo.total();
+  double* tmp = nullptr;
+  FDB_CUDA(cudaMalloc(&tmp, (size_t)total * sizeof(double)));
+  // reference extents (e0,e1,e2) padded on the left so that permute210 applies
+  int64_t e0 = 1, e1 = 1, e2 = 1;
+  if (h->ndims == 3) { e0 = h->dims[0]; e1 = h->dims[1]; e2 = h->dims[2]; }
+  else { e0 = h->dims[0]; e1 = 1; e2 = h->dims[1]; }
+  int rc = FDB_OK;
+  if (upload) {
+    // host col-major == row-major (e2, e1, e0) -> device row-major (e0, e1, e2)
+    FDB_TRY(field_sync(f));
+    cudaError_t ce = cudaMemcpyAsync(tmp, host, (size_t)total * sizeof(double), cudaMemcpyHostToDevice, s.s_main);
+    if (ce != cudaSuccess) { cudaFree(tmp); return set_error(FDB_E_CUDA, "H2D copy: %s", cudaGetErrorString(ce)); }
+    rc = launch_permute(tmp, f->body(0, which_buf), e2, e1, e0, s.s_main);
+  } else {
+    rc = launch_permute(f->body(0, which_buf), tmp, e0, e1, e2, s.s_main);
+    if (rc == FDB_OK) {
+      cudaError_t ce = cudaMemcpyAsync(host, tmp, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, s.s_main);
+      if (ce != cudaSuccess) rc = set_error(FDB_E_CUDA, "D2H copy: %s", cudaGetErrorString(ce));
+    }
+  }
+  cudaStreamSynchronize(s.s_main);
+  cudaFree(tmp);
+  return rc;
+}
+
+int fdb_stencil_set_input(fdb_stencil* h, const double* host_field, int layout) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_field) return set_error(FDB_E_INVALID, "null argument");
+  Field* f = &h->field;
+  if (layout == FDB_ROW_MAJOR) {
+    FDB_TRY(field_upload(f, f->cur, host_field, nullptr));
+  } else if (layout == FDB_COL_MAJOR) {
+    FDB_TRY(stencil_colmajor_io(h, f->cur, const_cast<double*>(host_field), true));
+    // publish (records events, refreshes ghosts)
+    for (auto& s : f->slabs) {
+      FDB_CUDA(cudaSetDevice(s.device));
+      FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
+    }
+  } else {
+    return set_error(FDB_E_INVALID, "unknown layout %d", layout);
+  }
+  h->out_valid = false;
+  return field_sync(f);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_set_input_slab(fdb_stencil* h, const double* host_slab) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
+  FDB_TRY(field_upload(&h->field, h->field.cur, nullptr, host_slab));
+  h->out_valid = false;
+  return field_sync(&h->field);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_get_kernel(const fdb_stencil* h, int* kernel) {
+  if (!h || !kernel) return set_error(FDB_E_INVALID, "null argument");
+  const bool can = stencil_lap7_supported(h->field, h->br);
+  *kernel = (h->kernel == FDB_KERNEL_GENERIC || !can) ? FDB_KERNEL_GENERIC : FDB_KERNEL_TMA;
+  return FDB_OK;
+}
+
+int fdb_stencil_set_kernel(fdb_stencil* h, int kernel) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (kernel != FDB_KERNEL_AUTO && kernel != FDB_KERNEL_GENERIC && kernel != FDB_KERNEL_TMA)
+    return set_error(FDB_E_INVALID, "unknown kernel id %d", kernel);
+  if (kernel == FDB_KERNEL_TMA && !stencil_lap7_supported(h->field, h->br))
+    return set_error(FDB_E_INVALID, "the TMA kernel only runs the 3-D 7-point stencil with an even last extent");
+  h->kernel = kernel;
+  return FDB_OK;
+}
+
+int fdb_stencil_set_stream(fdb_stencil* h, void* cuda_stream) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  return field_set_stream(&h->field, cuda_stream);
+  FDB_GUARD_END
+}
+
+static int stencil_apply_async(fdb_stencil* h) {
+  Field* f = &h->field;
+  StencilSweep sw;
+  sw.b = &h->br;
+  int kern = FDB_KERNEL_GENERIC;
+  FDB_TRY(fdb_stencil_get_kernel(h, &kern));
+  sw.fast = (kern == FDB_KERNEL_TMA);
+  FDB_TRY(field_sweep(f, &sw));
+  h->out_valid = true;
+  return FDB_OK;
+}
+
+// The sweep also exchanged the ghosts of the output buffer, so the O(1) swap
+// leaves a fully valid input field (ref: copyOutToIn, Filter.cpp:440-463, which
+// copies the block and repacks every window).
+static int stencil_swap(fdb_stencil* h) {
+  if (!h->out_valid) return FDB_OK;  // in == out already (nothing applied since the last swap)
+  h->field.cur = 1 - h->field.cur;
+  h->out_valid = false;
+  return FDB_OK;
+}
+
+int fdb_stencil_apply(fdb_stencil* h) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  Field* f = &h->field;
+  FDB_TRY(timing_begin(f));
+  FDB_TRY(stencil_apply_async(h));
+  FDB_TRY(timing_end(f));
+  f->last_updates = (double)f->geo.total();
+  FDB_TRY(field_sync(f));
+  return timing_collect(f);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_swap(fdb_stencil* h) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  return stencil_swap(h);
+}
+
+int fdb_stencil_iterate(fdb_stencil* h, int64_t niter) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (niter < 0) return set_error(FDB_E_INVALID, "negative iteration count");
+  Field* f = &h->field;
+  FDB_TRY(timing_begin(f));
+  for (int64_t it = 0; it < niter; ++it) {
+    FDB_TRY(stencil_apply_async(h));
+    FDB_TRY(stencil_swap(h));
+  }
+  FDB_TRY(timing_end(f));
+  f->last_updates = (double)niter * (double)f->geo.total();
+  FDB_TRY(field_sync(f));
+  return timing_collect(f);
+  FDB_GUARD_END
+}
+
+// after a swap "output" reads as the same data as "input" (copyOutToIn semantics)
+static int stencil_buffer(const fdb_stencil* h, int which, int* p) {
+  if (which != FDB_INPUT && which != FDB_OUTPUT) return set_error(FDB_E_INVALID, "which must be FDB_INPUT or FDB_OUTPUT");
+  *p = (which == FDB_OUTPUT && h->out_valid) ? 1 - h->field.cur : h->field.cur;
+  return FDB_OK;
+}
+
+int fdb_stencil_checksum(fdb_stencil* h, int which, double* sum) {
+  FDB_GUARD_BEGIN
+  if (!h || !sum) return set_error(FDB_E_INVALID, "null argument");
+  int p = 0;
+  FDB_TRY(stencil_buffer(h, which, &p));
+  return field_sum(&h->field, p, sum);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_get(fdb_stencil* h, int which, double* host_field, int layout) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_field) return set_error(FDB_E_INVALID, "null argument");
+  int p = 0;
+  FDB_TRY(stencil_buffer(h, which, &p));
+  if (layout == FDB_ROW_MAJOR) return field_download(&h->field, p, host_field, nullptr);
+  if (layout == FDB_COL_MAJOR) return stencil_colmajor_io(h, p, host_field, false);
+  return set_error(FDB_E_INVALID, "unknown layout %d", layout);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_get_slab(fdb_stencil* h, int which, double* host_slab) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
+  int p = 0;
+  FDB_TRY(stencil_buffer(h, which, &p));
+  return field_download(&h->field, p, nullptr, host_slab);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_last_timing(const fdb_stencil* h, double* gpu_ms, double* cell_updates,
+                            double* halo_bytes) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (gpu_ms) *gpu_ms = h->field.last_ms;
+  if (cell_updates) *cell_updates = h->field.last_updates;
+  if (halo_bytes) *halo_bytes = h->field.last_halo_bytes / (double)h->field.ngpus;
+  return FDB_OK;
+}
+
+int fdb_stencil_destroy(fdb_stencil* h) {
+  if (!h) return FDB_OK;
+  field_destroy(&h->field);
+  delete h;
+  return FDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// fdb_internal.h -- shared declarations of the fidib200 runtime (not part of the ABI).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "fidib200.h"
+
+namespace fdb {
+
+// ---- errors -----------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+#define FDB_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::fdb::set_error(_e == cudaErrorMemoryAllocation ? FDB_E_OOM : FDB_E_CUDA,    \
+                              "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                              __FILE__, __LINE__);                                        \
+  } while (0)
+
+#define FDB_NCCL(expr)                                                                    \
+  do {                                                                                    \
+    ncclResult_t _r = (expr);                                                             \
+    if (_r != ncclSuccess)                                                                \
+      return ::fdb::set_error(FDB_E_NCCL, "%s failed: %s (%s:%d)", #expr,                 \
+                              ncclGetErrorString(_r), __FILE__, __LINE__);                \
+  } while (0)
+
+#define FDB_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != FDB_OK) return _rc; \
+  } while (0)
+
+void count_launch(int64_t n = 1);
+int64_t launch_count();
+
+// ---- geometry of one engine -------------------------------------------------
+// Every problem is carried as a 3-D row-major box (n0, n1, n2), n2 fastest.
+// ndims == 2 maps (d0, d1) -> (d0, 1, d1) and ndims == 1 maps (d0) -> (1, 1, d0),
+// so the reference's last axis is always the contiguous one and its first axis
+// (when it exists beside another) is the slab axis.  `axis_of[j]` is the
+// internal axis of reference axis j.
+struct Geometry {
+  int ndims = 3;
+  int64_t n[3] = {1, 1, 1};
+  int axis_of[3] = {0, 1, 2};
+  bool active[3] = {true, true, true};
+  int64_t plane() const { return n[1] * n[2]; }
+  int64_t total() const { return n[0] * n[1] * n[2]; }
+};
+int make_geometry(int ndims, const int64_t* dims, Geometry* g);
+
+// ---- communicator (one process per GPU) -------------------------------------
+}  // namespace fdb
+
+struct fdb_comm {
+  int rank = 0, nranks = 1, device = 0;
+  ncclComm_t nccl = nullptr;
+  cudaStream_t stream = nullptr;  // small collectives (checksum gather, barrier)
+  double* scratch = nullptr;      // device scratch for those collectives
+  size_t scratch_doubles = 0;
+};
+
+namespace fdb {
+
+// ---- one device's share of a field -------------------------------------------
+// Buffer layout (doubles): [G ghost planes below][nloc planes][G ghost planes above]
+struct Slab {
+  int device = 0;
+  int64_t lo = 0, hi = 0;  // global plane range on axis 0
+  int64_t nloc() const { return hi - lo; }
+  double* buf[2] = {nullptr, nullptr};  // ping-pong, each (nloc + 2G) planes
+  double* partial = nullptr;            // reduction scratch
+  double* plane_sums = nullptr;         // nloc doubles
+  cudaStream_t s_main = nullptr, s_bnd = nullptr;
+  bool own_main = true;
+  cudaEvent_t ev_local_done = nullptr;              // all of the current field written
+  cudaEvent_t ev_bnd_done = nullptr;                // boundary planes of the next field written
+  cudaEvent_t ev_ghost_ready[2] = {nullptr, nullptr};  // ghosts of buf[p] filled
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;     // timing
+  // TMA descriptors, index = buffer parity
+  // (several box shapes over the same tensors, see kernels_tma.cu)
+  CUtensorMap tm_body[2];  // local planes, box = tile rows
+  CUtensorMap tm_row[2];   // local planes, box = one (halo) row
+  CUtensorMap tm_col[2];   // local planes, box = 2 cells x tile rows (k wrap)
+  CUtensorMap tm_glo[2];   // the G planes below local plane 0 (ghost, or wrap for 1 device)
+  CUtensorMap tm_ghi[2];   // the G planes above local plane nloc-1
+  bool have_tma = false;
+};
+
+// A field decomposed in slabs over the devices this process drives, plus the
+// halo plumbing between them (peer copies in-process, NCCL between processes).
+struct Field {
+  Geometry geo;
+  int G = 1;                // ghost planes per side
+  bool need_lo = true;      // someone reads plane i-1.. (ghost below)
+  bool need_hi = false;     // someone reads plane i+1.. (ghost above)
+  int ngpus = 1;            // devices in this process
+  fdb_comm* comm = nullptr; // non-null: one slab here, neighbours are other ranks
+  int nparts = 1;           // total slabs in the ring
+  std::vector<Slab> slabs;
+  int cur = 0;              // buf[cur] holds the current field
+  bool ghosts_valid = false;
+  double last_ms = 0, last_updates = 0, last_halo_bytes = 0;
+
+  double* body(int d, int p) const { return slabs[d].buf[p] + (int64_t)G * geo.plane(); }
+  double* ghost_lo(int d, int p) const;  // G planes below local plane 0 (never null)
+  double* ghost_hi(int d, int p) const;  // G planes above local plane nloc-1
+  bool single() const { return nparts == 1; }
+};
+
+int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_hi, int ngpus,
+                 fdb_comm* comm, bool want_tma);
+void field_destroy(Field* f);
+int field_set_stream(Field* f, void* stream);
+int field_upload(Field* f, int p, const double* host_global, const double* host_slab);
+int field_download(Field* f, int p, double* host_global, double* host_slab);
+int field_fill_delta(Field* f, int p);
+// (re)fill the ghosts of buf[p] from the neighbours' boundary planes; enqueued on
+// the boundary streams, ev_ghost_ready[p] recorded.  `after_bnd` = wait for
+// ev_bnd_done (the planes were just produced by a boundary kernel) instead of
+// ev_local_done.
+int field_exchange(Field* f, int p, bool after_bnd);
+int field_sync(Field* f);
+// deterministic, partition-invariant reductions: per-plane tree sums on the
+// device, then a sequential sum over planes in global order (collective in
+// dist mode, every rank gets the result)
+int field_sum(Field* f, int p, double* out);
+int field_sqdev(Field* f, int p, double mean, double* out);
+
+// one sweep of a stencil kernel over every slab: boundary planes first (their
+// halos start travelling while the interior is computed), ghosts of the new
+// field exchanged, buffers not swapped.  `launch(d, ibeg, iend, stream)` must
+// enqueue the kernel computing local planes [ibeg,iend) of buf[1-cur] from buf[cur].
+struct SweepLauncher {
+  virtual int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) = 0;
+  virtual ~SweepLauncher() {}
+};
+int field_sweep(Field* f, SweepLauncher* L);
+
+// ---- kernels ----------------------------------------------------------------
+struct UpwindCoeffs {
+  double c[3];   // ((dt*v)*up)/delta per internal axis (0 where inactive)
+  int up[3];     // -1 / +1 upwind direction per internal axis
+  bool active[3];
+};
+
+int launch_upwind_generic(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                          cudaStream_t s);
+bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k);
+int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                      cudaStream_t s);
+
+struct StencilBranches {
+  int nbranch = 0;
+  int off[32][3];   // internal-axis offsets, already in application order
+  double w[32];
+};
+int launch_stencil_generic(const Field& f, int d, int64_t ibeg, int64_t iend,
+                           const StencilBranches& b, cudaStream_t s);
+bool stencil_lap7_supported(const Field& f, const StencilBranches& b);
+int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const StencilBranches& b,
+                        cudaStream_t s);
+
+int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode, double mean,
+                      double* partial, double* plane_sums, cudaStream_t s);
+int64_t reduce_partials_per_plane(int64_t plane);
+int launch_fill(double* p, int64_t n, double v, cudaStream_t s);
+int launch_permute(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, cudaStream_t s);
+
+int encode_tensor_map_3d(CUtensorMap* tm, const double* base, int64_t n2, int64_t n1, int64_t n0,
+                         int box2, int box1);
+
+}  // namespace fdb

@@ -1,0 +1,357 @@
+// kernels_tma.cu -- the sm_100a hot kernels: TMA-staged shared-memory tile pipelines
+// for the 3-D upwind step and the 3-D 7-point Laplacian apply.
+//
+// Shape of both kernels (HBM-bound FP64 stencils, no tensor cores):
+//   * persistent CTAs, grid = resident CTAs per SM x SM count, static round-robin
+//     over work items (i-chunk, j-tile, k-tile);
+//   * one producer warp: an elected lane streams the tile of each i-plane into a
+//     ring of shared-memory stages with cp.async.bulk.tensor (TMA) and arms the
+//     stage's "full" mbarrier with the expected byte count;
+//   * consumer warps: wait on "full", pull the plane's tile into registers with
+//     128-bit LDS, release the stage ("empty" mbarrier), then compute and store
+//     coalesced 128-bit rows.  Planes i-1 (and i+1 for the Laplacian) are carried
+//     in registers while the CTA marches along axis 0, so every cell of the field
+//     crosses L2->SM once (plus tile halos);
+//   * periodic wrap: rows/columns that fall off the tile grid are fetched by
+//     separate small TMA boxes from the far side of the domain (TMA's own
+//     out-of-bounds fill is zero, not periodic); planes below/above the slab come
+//     from the ghost tensors (which alias the far planes on a single device).
+//
+// Arithmetic contract: as kernels_generic.cu (separately rounded mul/add, reference
+// order), so this path is bit-identical to the generic one and to the oracle.
+#include "fdb_internal.h"
+
+namespace fdb {
+
+namespace {
+
+// ---- PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// All shared-memory traffic below is addressed with 32-bit shared-window
+// addresses so that ptxas emits LDS/SYNCS (a generic pointer rebuilt from an
+// integer would turn every tile read into a generic LD).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ double2 lds_v2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void st_global_v2(double* p, double x, double y) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+
+// ---- upwind tile configuration ------------------------------------------------
+// Tile = BJ rows x BK cells of one i-plane; each consumer thread owns R
+// consecutive rows x 2 consecutive cells (one double2 per row).
+template <int BJ_, int BK_, int R_, int STAGES_>
+struct UpwindCfg {
+  static constexpr int BJ = BJ_, BK = BK_, R = R_, STAGES = STAGES_;
+  static constexpr int BKH = BK + 2;              // row pitch in doubles: 2 halo cells + BK
+  static constexpr int TX = BK / 2;               // threads along k
+  static constexpr int TY = BJ / R;               // thread rows
+  static constexpr int CONSUMERS = TX * TY;
+  static constexpr int CONSUMER_WARPS = CONSUMERS / 32;
+  static constexpr int THREADS = CONSUMERS + 32;  // + producer warp
+  static constexpr int ROW_BYTES = BKH * 8;
+  static constexpr int HALO_BYTES = (ROW_BYTES + 127) / 128 * 128;  // slot of row j0-1
+  static constexpr int BODY_BYTES = BJ * ROW_BYTES;                 // rows j0..j0+BJ-1
+  static constexpr int WRAP_BYTES = BJ * 16;                        // cells N2-2,N2-1 of each row
+  static constexpr int BODY_OFF = HALO_BYTES;
+  static constexpr int WRAP_OFF = (BODY_OFF + BODY_BYTES + 127) / 128 * 128;
+  static constexpr int STAGE_BYTES = (WRAP_OFF + WRAP_BYTES + 127) / 128 * 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+  static_assert(BJ % R == 0 && BK % 2 == 0 && CONSUMERS % 32 == 0, "bad tile");
+  static_assert(BODY_BYTES % 128 == 0, "TMA destination must stay 128-byte aligned");
+  static_assert(BKH <= 256 && BJ <= 256, "TMA box limit");
+};
+
+struct UpwindTmaArgs {
+  double* out;          // local plane 0 of the output field
+  int64_t n1, n2;       // plane extents
+  int64_t ibeg, iend;   // local planes to compute
+  int ci;               // planes per work item
+  int njt, nkt;         // tiles per plane
+  int64_t nwork;        // work items
+  int G;                // ghost depth of the ghost tensor (its last plane is local plane -1)
+  double c0, c1, c2;
+};
+
+// Tensor maps of the input field, by box shape:
+//   tm_body : local planes,  box {BKH, BJ, 1}   (tile rows)
+//   tm_row  : local planes,  box {BKH, 1, 1}    (halo row j0-1, wrapped)
+//   tm_col  : local planes,  box {2, BJ, 1}     (cells N2-2..N2-1: wrap of k = -1)
+//   tm_glo  : ghost planes below local plane 0, box {BKH, BJ, 1}
+template <class C>
+__global__ void __launch_bounds__(C::THREADS)
+    upwind3d_tma_kernel(const __grid_constant__ CUtensorMap tm_body,
+                        const __grid_constant__ CUtensorMap tm_row,
+                        const __grid_constant__ CUtensorMap tm_col,
+                        const __grid_constant__ CUtensorMap tm_glo, const UpwindTmaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // dynamic smem is only guaranteed 16-byte aligned: round up to 128 by hand
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t full = smem + C::STAGES * C::STAGE_BYTES;  // STAGES x 8-byte mbarriers
+  const uint32_t empty = full + C::STAGES * 8;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    // ===================== producer warp =====================
+    if ((tid & 31) == 0) {
+      prefetch_tmap(&tm_body);
+      prefetch_tmap(&tm_row);
+      prefetch_tmap(&tm_col);
+      prefetch_tmap(&tm_glo);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+        const int kt = (int)(w % a.nkt);
+        const int jt = (int)((w / a.nkt) % a.njt);
+        const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+        const int64_t i0 = a.ibeg + ic * a.ci;
+        const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+        const int k0 = kt * C::BK - 2;  // box starts 2 cells left of the tile (16 B aligned)
+        const int j0 = jt * C::BJ;
+        const int jm = (j0 == 0) ? (int)a.n1 - 1 : j0 - 1;  // periodic row j0-1
+        for (int64_t i = i0 - 1; i < i1; ++i) {
+          mbar_wait(empty + 8 * stage, phase ^ 1);
+          const uint32_t st = smem + stage * C::STAGE_BYTES;
+          const uint32_t fb = full + 8 * stage;
+          if (i == i0 - 1) {
+            // plane below the chunk: only its tile rows are needed (register carry)
+            mbar_expect_tx(fb, C::BODY_BYTES);
+            if (i < 0)
+              tma_load_3d(st + C::BODY_OFF, &tm_glo, fb, k0, j0, a.G - 1);
+            else
+              tma_load_3d(st + C::BODY_OFF, &tm_body, fb, k0, j0, (int)i);
+          } else {
+            const uint32_t bytes = C::BODY_BYTES + C::ROW_BYTES + (kt == 0 ? C::WRAP_BYTES : 0);
+            mbar_expect_tx(fb, bytes);
+            tma_load_3d(st + C::BODY_OFF, &tm_body, fb, k0, j0, (int)i);
+            tma_load_3d(st, &tm_row, fb, k0, jm, (int)i);
+            if (kt == 0) tma_load_3d(st + C::WRAP_OFF, &tm_col, fb, (int)a.n2 - 2, j0, (int)i);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  const int tx = tid % C::TX;
+  const int ty = tid / C::TX;
+  const int r0 = ty * C::R;
+  const int lane = tid & 31;
+  int stage = 0;
+  uint32_t phase = 0;
+  const double c0 = a.c0, c1 = a.c1, c2 = a.c2;
+
+  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    const int kt = (int)(w % a.nkt);
+    const int jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    const int64_t k = (int64_t)kt * C::BK + 2 * tx;
+    const int64_t j = (int64_t)jt * C::BJ + r0;
+    const bool k_ok = k < a.n2;
+    const bool wrap_lane = (kt == 0) && (tx == 0);
+
+    double2 below[C::R];  // plane i-1, this thread's cells
+    {
+      mbar_wait(full + 8 * stage, phase);
+      const uint32_t st = smem + stage * C::STAGE_BYTES;
+#pragma unroll
+      for (int r = 0; r < C::R; ++r)
+        below[r] = lds_v2(st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES + (2 + 2 * tx) * 8);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    for (int64_t i = i0; i < i1; ++i) {
+      mbar_wait(full + 8 * stage, phase);
+      const uint32_t st = smem + stage * C::STAGE_BYTES;
+      double2 ctr[C::R];
+      double km1[C::R];
+      // row j-1 of the thread's first row: the halo slot for the tile's first row
+      const uint32_t up_row = (r0 == 0) ? st : st + C::BODY_OFF + (r0 - 1) * C::ROW_BYTES;
+      const double2 up = lds_v2(up_row + (2 + 2 * tx) * 8);
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        const uint32_t row = st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES;
+        ctr[r] = lds_v2(row + (2 + 2 * tx) * 8);
+        km1[r] = lds_f64(wrap_lane ? st + C::WRAP_OFF + (r0 + r) * 16 + 8 : row + (1 + 2 * tx) * 8);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+
+      double* orow = a.out + (i * a.n1 + j) * a.n2 + k;
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        const double2 jm = (r == 0) ? up : ctr[r - 1];
+        // ref: upwind.cxx:72-80, axes 0,1,2 in order, no FMA
+        double x = ctr[r].x;
+        x = __dsub_rn(x, __dmul_rn(c0, __dsub_rn(below[r].x, ctr[r].x)));
+        x = __dsub_rn(x, __dmul_rn(c1, __dsub_rn(jm.x, ctr[r].x)));
+        x = __dsub_rn(x, __dmul_rn(c2, __dsub_rn(km1[r], ctr[r].x)));
+        double y = ctr[r].y;
+        y = __dsub_rn(y, __dmul_rn(c0, __dsub_rn(below[r].y, ctr[r].y)));
+        y = __dsub_rn(y, __dmul_rn(c1, __dsub_rn(jm.y, ctr[r].y)));
+        y = __dsub_rn(y, __dmul_rn(c2, __dsub_rn(ctr[r].x, ctr[r].y)));
+        if (k_ok && (j + r) < a.n1) st_global_v2(orow + (int64_t)r * a.n2, x, y);
+        below[r] = ctr[r];
+      }
+    }
+  }
+}
+
+using UpCfg = UpwindCfg<16, 128, 4, 6>;
+
+struct KernelAttr {
+  bool done = false;
+  int ctas_per_sm = 1;
+  int sms = 148;
+};
+KernelAttr g_up_attr[16];  // per device
+
+}  // namespace
+
+// Encode every tensor map slab d needs (both ping-pong buffers).  Leaves
+// have_tma = false when the row pitch is not a multiple of 16 bytes (odd n2).
+int tma_encode_slab(Field* f, int d) {
+  using C = UpCfg;
+  Slab& s = f->slabs[d];
+  s.have_tma = false;
+  const int64_t n1 = f->geo.n[1], n2 = f->geo.n[2];
+  if (f->geo.ndims != 3 || n2 % 2 != 0 || n2 < 4) return FDB_OK;
+  FDB_CUDA(cudaSetDevice(s.device));
+  for (int p = 0; p < 2; ++p) {
+    FDB_TRY(encode_tensor_map_3d(&s.tm_body[p], f->body(d, p), n2, n1, s.nloc(), C::BKH, C::BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_row[p], f->body(d, p), n2, n1, s.nloc(), C::BKH, 1));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_col[p], f->body(d, p), n2, n1, s.nloc(), 2, C::BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_glo[p], f->ghost_lo(d, p), n2, n1, f->G, C::BKH, C::BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_ghi[p], f->ghost_hi(d, p), n2, n1, f->G, C::BKH, C::BJ));
+  }
+  s.have_tma = true;
+  return FDB_OK;
+}
+
+bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k) {
+  if (f.geo.ndims != 3) return false;
+  if (!f.slabs.empty() && !f.slabs[0].have_tma) return false;
+  if (k.up[0] != -1 || k.up[1] != -1 || k.up[2] != -1) return false;
+  if (f.geo.n[2] % 2 != 0 || f.geo.n[2] < 4) return false;  // 16-byte row pitch, wrap box of 2 cells
+  if (f.geo.n[1] < 2) return false;
+  return true;
+}
+
+int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                      cudaStream_t s) {
+  if (iend <= ibeg) return FDB_OK;
+  using C = UpCfg;
+  const Slab& sl = f.slabs[d];
+  KernelAttr& at = g_up_attr[sl.device & 15];
+  if (!at.done) {
+    FDB_CUDA(cudaFuncSetAttribute(upwind3d_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
+    int nb = 0;
+    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, upwind3d_tma_kernel<C>, C::THREADS,
+                                                           C::SMEM_BYTES));
+    cudaDeviceProp prop;
+    FDB_CUDA(cudaGetDeviceProperties(&prop, sl.device));
+    at.ctas_per_sm = nb < 1 ? 1 : nb;
+    at.sms = prop.multiProcessorCount;
+    at.done = true;
+  }
+  UpwindTmaArgs a;
+  a.out = f.body(d, 1 - f.cur);
+  a.n1 = f.geo.n[1];
+  a.n2 = f.geo.n[2];
+  a.ibeg = ibeg;
+  a.iend = iend;
+  a.njt = (int)((a.n1 + C::BJ - 1) / C::BJ);
+  a.nkt = (int)((a.n2 + C::BK - 1) / C::BK);
+  a.G = f.G;
+  a.c0 = k.c[0];
+  a.c1 = k.c[1];
+  a.c2 = k.c[2];
+  // i-chunk: long enough to amortise the extra plane each work item reads,
+  // short enough that every CTA gets several items (static round-robin).
+  const int64_t grid_max = (int64_t)at.ctas_per_sm * at.sms;
+  const int64_t tiles = (int64_t)a.njt * a.nkt;
+  const int64_t planes = iend - ibeg;
+  int64_t ci = 64;
+  while (ci > 4 && tiles * ((planes + ci - 1) / ci) < 8 * grid_max) ci /= 2;
+  if (ci > planes) ci = planes;
+  a.ci = (int)ci;
+  a.nwork = tiles * ((planes + ci - 1) / ci);
+  const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  const int p = f.cur;
+  upwind3d_tma_kernel<C><<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, s>>>(
+      sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p], a);
+  count_launch();
+  FDB_CUDA(cudaGetLastError());
+  return FDB_OK;
+}
+
+bool stencil_lap7_supported(const Field&, const StencilBranches&) { return false; }
+int launch_stencil_lap7(const Field&, int, int64_t, int64_t, const StencilBranches&, cudaStream_t) {
+  return set_error(FDB_E_STATE, "laplacian TMA kernel not built yet");
+}
+
+}  // namespace fdb

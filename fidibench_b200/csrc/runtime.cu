@@ -1,0 +1,444 @@
+// runtime.cu -- device context of the fidib200 engines: slab-decomposed fields,
+// streams/events, halo exchange (peer copies in one process, NCCL send/recv
+// between processes), uploads/downloads and the host side of the reductions.
+//
+// Replaces, B200-first, what the reference spreads over CubeDecomp
+// (cxx/CubeDecomp.cpp:11-131), Filter's MPI-3 RMA windows (cxx/Filter.cpp:114-129,
+// :320-340) and copyOutToIn's window repacking (:440-463): slabs along axis 0 make
+// every halo a contiguous run of planes, received straight into the ghost planes
+// of the field allocation.
+#include "fdb_internal.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace fdb {
+
+// ---- errors / counters ----------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+const char* last_error() { return g_err; }
+
+static int64_t g_launches = 0;
+void count_launch(int64_t n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED); }
+int64_t launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+// ---- geometry ---------------------------------------------------------------------
+int make_geometry(int ndims, const int64_t* dims, Geometry* g) {
+  if (ndims < 1 || ndims > 3) return set_error(FDB_E_INVALID, "ndims must be 1, 2 or 3 (got %d)", ndims);
+  if (!dims) return set_error(FDB_E_INVALID, "null dimensions");
+  for (int j = 0; j < ndims; ++j)
+    if (dims[j] < 1) return set_error(FDB_E_INVALID, "extent %d is %lld", j, (long long)dims[j]);
+  *g = Geometry();
+  g->ndims = ndims;
+  if (ndims == 3) {
+    for (int j = 0; j < 3; ++j) { g->n[j] = dims[j]; g->axis_of[j] = j; }
+  } else if (ndims == 2) {
+    g->n[0] = dims[0]; g->n[1] = 1; g->n[2] = dims[1];
+    g->axis_of[0] = 0; g->axis_of[1] = 2;
+    g->active[1] = false;
+  } else {
+    g->n[0] = 1; g->n[1] = 1; g->n[2] = dims[0];
+    g->axis_of[0] = 2;
+    g->active[0] = g->active[1] = false;
+  }
+  return FDB_OK;
+}
+
+// ---- tensor maps ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 3-D FP64 tensor (n0 planes x n1 rows x n2 cells, n2 contiguous), box {box2, box1, 1}
+int encode_tensor_map_3d(CUtensorMap* tm, const double* base, int64_t n2, int64_t n1, int64_t n0,
+                         int box2, int box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(FDB_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)n2, (cuuint64_t)n1, (cuuint64_t)n0};
+  cuuint64_t strides[2] = {(cuuint64_t)n2 * 8, (cuuint64_t)n2 * (cuuint64_t)n1 * 8};
+  cuuint32_t box[3] = {(cuuint32_t)box2, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(FDB_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lldx%lld box=%dx%d",
+                     (int)r, (long long)n0, (long long)n1, (long long)n2, box1, box2);
+  return FDB_OK;
+}
+
+// ---- field --------------------------------------------------------------------------
+double* Field::ghost_lo(int d, int p) const {
+  if (single()) return body(d, p) + (slabs[d].nloc() - G) * geo.plane();  // periodic alias
+  return slabs[d].buf[p];
+}
+double* Field::ghost_hi(int d, int p) const {
+  if (single()) return body(d, p);  // periodic alias
+  return body(d, p) + slabs[d].nloc() * geo.plane();
+}
+
+int tma_encode_slab(Field* f, int d);  // kernels_tma.cu
+
+int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_hi, int ngpus,
+                 fdb_comm* comm, bool want_tma) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return set_error(FDB_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  f->geo = geo;
+  f->G = G;
+  f->need_lo = need_lo;
+  f->need_hi = need_hi;
+  f->comm = comm;
+  f->cur = 0;
+  if (comm) {
+    f->ngpus = 1;
+    f->nparts = comm->nranks;
+  } else {
+    if (ngpus < 1) return set_error(FDB_E_INVALID, "ngpus must be >= 1 (got %d)", ngpus);
+    if (ngpus > ndev)
+      return set_error(FDB_E_INVALID, "ngpus=%d but only %d CUDA device(s) visible", ngpus, ndev);
+    f->ngpus = ngpus;
+    f->nparts = ngpus;
+  }
+  if (geo.n[0] % f->nparts != 0)
+    return set_error(FDB_E_DECOMP,
+                     "No valid domain decomposition: %d slab(s) do not divide the %lld planes of axis 0",
+                     f->nparts, (long long)geo.n[0]);
+  const int64_t nloc = geo.n[0] / f->nparts;
+  if (nloc < G)
+    return set_error(FDB_E_DECOMP, "slabs of %lld plane(s) are thinner than the %d ghost plane(s)",
+                     (long long)nloc, G);
+  const int64_t plane = geo.plane();
+  f->slabs.assign(f->ngpus, Slab());
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    const int part = comm ? comm->rank : d;
+    s.device = comm ? comm->device : d;
+    s.lo = part * nloc;
+    s.hi = s.lo + nloc;
+    FDB_CUDA(cudaSetDevice(s.device));
+    const size_t bytes = (size_t)(nloc + 2 * G) * (size_t)plane * sizeof(double);
+    for (int p = 0; p < 2; ++p) {
+      FDB_CUDA(cudaMalloc(&s.buf[p], bytes));
+      FDB_CUDA(cudaMemset(s.buf[p], 0, bytes));
+    }
+    const int64_t nchunk = reduce_partials_per_plane(plane);
+    FDB_CUDA(cudaMalloc(&s.partial, (size_t)(nloc * nchunk) * sizeof(double)));
+    FDB_CUDA(cudaMalloc(&s.plane_sums, (size_t)nloc * sizeof(double)));
+    int lo_prio = 0, hi_prio = 0;
+    FDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    FDB_CUDA(cudaStreamCreateWithPriority(&s.s_main, cudaStreamNonBlocking, lo_prio));
+    FDB_CUDA(cudaStreamCreateWithPriority(&s.s_bnd, cudaStreamNonBlocking, hi_prio));
+    s.own_main = true;
+    FDB_CUDA(cudaEventCreateWithFlags(&s.ev_local_done, cudaEventDisableTiming));
+    FDB_CUDA(cudaEventCreateWithFlags(&s.ev_bnd_done, cudaEventDisableTiming));
+    FDB_CUDA(cudaEventCreateWithFlags(&s.ev_ghost_ready[0], cudaEventDisableTiming));
+    FDB_CUDA(cudaEventCreateWithFlags(&s.ev_ghost_ready[1], cudaEventDisableTiming));
+    FDB_CUDA(cudaEventCreate(&s.ev_t0));
+    FDB_CUDA(cudaEventCreate(&s.ev_t1));
+    FDB_CUDA(cudaDeviceSynchronize());  // memsets done before anything else touches the buffers
+    FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
+    FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[0], s.s_bnd));
+    FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[1], s.s_bnd));
+  }
+  // peer access between neighbouring devices of this process
+  if (!comm && f->ngpus > 1) {
+    for (int d = 0; d < f->ngpus; ++d) {
+      FDB_CUDA(cudaSetDevice(f->slabs[d].device));
+      for (int o : {(d + 1) % f->ngpus, (d + f->ngpus - 1) % f->ngpus}) {
+        if (o == d) continue;
+        int can = 0;
+        FDB_CUDA(cudaDeviceCanAccessPeer(&can, f->slabs[d].device, f->slabs[o].device));
+        if (can) {
+          cudaError_t pe = cudaDeviceEnablePeerAccess(f->slabs[o].device, 0);
+          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+            return set_error(FDB_E_CUDA, "cudaDeviceEnablePeerAccess(%d->%d): %s", d, o,
+                             cudaGetErrorString(pe));
+          (void)cudaGetLastError();
+        }
+      }
+    }
+  }
+  if (want_tma) {
+    for (int d = 0; d < f->ngpus; ++d) FDB_TRY(tma_encode_slab(f, d));
+  }
+  return FDB_OK;
+}
+
+void field_destroy(Field* f) {
+  for (auto& s : f->slabs) {
+    cudaSetDevice(s.device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < 2; ++p) if (s.buf[p]) cudaFree(s.buf[p]);
+    if (s.partial) cudaFree(s.partial);
+    if (s.plane_sums) cudaFree(s.plane_sums);
+    if (s.s_main && s.own_main) cudaStreamDestroy(s.s_main);
+    if (s.s_bnd) cudaStreamDestroy(s.s_bnd);
+    for (cudaEvent_t ev : {s.ev_local_done, s.ev_bnd_done, s.ev_ghost_ready[0], s.ev_ghost_ready[1],
+                           s.ev_t0, s.ev_t1})
+      if (ev) cudaEventDestroy(ev);
+  }
+  f->slabs.clear();
+  (void)cudaGetLastError();
+}
+
+int field_set_stream(Field* f, void* stream) {
+  if (f->ngpus != 1)
+    return set_error(FDB_E_STATE, "a caller stream can only drive a single-device handle");
+  Slab& s = f->slabs[0];
+  FDB_CUDA(cudaSetDevice(s.device));
+  FDB_CUDA(cudaStreamSynchronize(s.s_main));
+  FDB_CUDA(cudaStreamSynchronize(s.s_bnd));
+  if (s.own_main) FDB_CUDA(cudaStreamDestroy(s.s_main));
+  if (stream) {
+    s.s_main = static_cast<cudaStream_t>(stream);
+    s.own_main = false;
+  } else {
+    int lo_prio = 0, hi_prio = 0;
+    FDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    FDB_CUDA(cudaStreamCreateWithPriority(&s.s_main, cudaStreamNonBlocking, lo_prio));
+    s.own_main = true;
+  }
+  FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
+  return FDB_OK;
+}
+
+int field_sync(Field* f) {
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_CUDA(cudaStreamSynchronize(s.s_main));
+    FDB_CUDA(cudaStreamSynchronize(s.s_bnd));
+  }
+  return FDB_OK;
+}
+
+// After a host-driven overwrite of buf[p] (upload, reset): publish it.
+static int field_publish(Field* f, int p) {
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
+  }
+  f->cur = p;
+  return field_exchange(f, p, /*after_bnd=*/false);
+}
+
+int field_upload(Field* f, int p, const double* host_global, const double* host_slab) {
+  FDB_TRY(field_sync(f));
+  const int64_t plane = f->geo.plane();
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    const double* src = host_global ? host_global + s.lo * plane
+                                    : host_slab + (s.lo - f->slabs[0].lo) * plane;
+    FDB_CUDA(cudaMemcpyAsync(f->body(d, p), src, (size_t)(s.nloc() * plane) * sizeof(double),
+                             cudaMemcpyHostToDevice, s.s_main));
+  }
+  return field_publish(f, p);
+}
+
+int field_download(Field* f, int p, double* host_global, double* host_slab) {
+  const int64_t plane = f->geo.plane();
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    double* dst = host_global ? host_global + s.lo * plane
+                              : host_slab + (s.lo - f->slabs[0].lo) * plane;
+    FDB_CUDA(cudaMemcpyAsync(dst, f->body(d, p), (size_t)(s.nloc() * plane) * sizeof(double),
+                             cudaMemcpyDeviceToHost, s.s_main));
+  }
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_CUDA(cudaStreamSynchronize(s.s_main));
+  }
+  return FDB_OK;
+}
+
+// ref: Upwind ctor, upwind.cxx:45-48 -- zero field, cell 0 = 1
+int field_fill_delta(Field* f, int p) {
+  FDB_TRY(field_sync(f));
+  const int64_t plane = f->geo.plane();
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_TRY(launch_fill(f->body(d, p), s.nloc() * plane, 0.0, s.s_main));
+    if (s.lo == 0) FDB_TRY(launch_fill(f->body(d, p), 1, 1.0, s.s_main));
+  }
+  return field_publish(f, p);
+}
+
+// Fill the ghosts of buf[p].  Pull model: the copy runs on the RECEIVING device's
+// boundary stream, so every event is recorded on the device that owns it.
+int field_exchange(Field* f, int p, bool after_bnd) {
+  if (f->single()) return FDB_OK;  // ghosts alias the far planes of the same buffer
+  const int64_t plane = f->geo.plane();
+  const size_t bytes = (size_t)f->G * (size_t)plane * sizeof(double);
+  const int64_t gcount = (int64_t)f->G * plane;
+  if (f->comm) {
+    Slab& s = f->slabs[0];
+    fdb_comm* c = f->comm;
+    FDB_CUDA(cudaSetDevice(s.device));
+    // the planes to send are produced on s_bnd (after_bnd) or were published on s_main
+    if (!after_bnd) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
+    const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
+    double* top = f->body(0, p) + (s.nloc() - f->G) * plane;
+    double* bottom = f->body(0, p);
+    FDB_NCCL(ncclGroupStart());
+    if (f->need_lo) {
+      FDB_NCCL(ncclSend(top, (size_t)gcount, ncclDouble, next, c->nccl, s.s_bnd));
+      FDB_NCCL(ncclRecv(f->ghost_lo(0, p), (size_t)gcount, ncclDouble, prev, c->nccl, s.s_bnd));
+    }
+    if (f->need_hi) {
+      FDB_NCCL(ncclSend(bottom, (size_t)gcount, ncclDouble, prev, c->nccl, s.s_bnd));
+      FDB_NCCL(ncclRecv(f->ghost_hi(0, p), (size_t)gcount, ncclDouble, next, c->nccl, s.s_bnd));
+    }
+    FDB_NCCL(ncclGroupEnd());
+    count_launch();
+    FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[p], s.s_bnd));
+    f->last_halo_bytes += (double)bytes * ((f->need_lo ? 1 : 0) + (f->need_hi ? 1 : 0));
+    return FDB_OK;
+  }
+  const int g = f->ngpus;
+  for (int d = 0; d < g; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    // WAR: this device's previous readers of ghost buffer p are done once its
+    // last sweep is (ev_local_done as recorded at the end of that sweep)
+    FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
+    if (f->need_lo) {
+      const int src = (d + g - 1) % g;
+      Slab& o = f->slabs[src];
+      FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, after_bnd ? o.ev_bnd_done : o.ev_local_done, 0));
+      FDB_CUDA(cudaMemcpyPeerAsync(f->ghost_lo(d, p), s.device,
+                                   f->body(src, p) + (o.nloc() - f->G) * plane, o.device, bytes,
+                                   s.s_bnd));
+    }
+    if (f->need_hi) {
+      const int src = (d + 1) % g;
+      Slab& o = f->slabs[src];
+      FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, after_bnd ? o.ev_bnd_done : o.ev_local_done, 0));
+      FDB_CUDA(cudaMemcpyPeerAsync(f->ghost_hi(d, p), s.device, f->body(src, p), o.device, bytes,
+                                   s.s_bnd));
+    }
+    FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[p], s.s_bnd));
+    f->last_halo_bytes += (double)bytes * ((f->need_lo ? 1 : 0) + (f->need_hi ? 1 : 0));
+  }
+  return FDB_OK;
+}
+
+// One sweep: buf[cur] -> buf[1-cur] on every slab (see fdb_internal.h).
+int field_sweep(Field* f, SweepLauncher* L) {
+  const int X = f->cur, Y = 1 - X;
+  if (f->single()) {
+    Slab& s = f->slabs[0];
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_TRY(L->launch(f, 0, 0, s.nloc(), s.s_main));
+    return FDB_OK;
+  }
+  // 1. boundary planes (the ones a neighbour needs) on the high-priority stream
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    const int64_t nloc = s.nloc();
+    const int64_t b_end = f->need_hi ? (f->G < nloc ? f->G : nloc) : 0;
+    const int64_t t_beg = f->need_lo ? (nloc - f->G > b_end ? nloc - f->G : b_end) : nloc;
+    FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
+    FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_ghost_ready[X], 0));
+    if (!f->comm) {
+      // WAR on the planes about to be rewritten: the neighbours' last pull of
+      // them (two sweeps ago, same buffer) must have finished.  NCCL sends are
+      // ordered by s_bnd itself.
+      const int g = f->ngpus;
+      if (f->need_lo) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[(d + 1) % g].ev_ghost_ready[Y], 0));
+      if (f->need_hi) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[(d + g - 1) % g].ev_ghost_ready[Y], 0));
+    }
+    FDB_TRY(L->launch(f, d, 0, b_end, s.s_bnd));
+    FDB_TRY(L->launch(f, d, t_beg, nloc, s.s_bnd));
+    FDB_CUDA(cudaEventRecord(s.ev_bnd_done, s.s_bnd));
+  }
+  // 2. their halos start travelling
+  FDB_TRY(field_exchange(f, Y, /*after_bnd=*/true));
+  // 3. interior, overlapped with the exchange
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    const int64_t nloc = s.nloc();
+    const int64_t b_end = f->need_hi ? (f->G < nloc ? f->G : nloc) : 0;
+    const int64_t t_beg = f->need_lo ? (nloc - f->G > b_end ? nloc - f->G : b_end) : nloc;
+    FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_ghost_ready[X], 0));
+    FDB_TRY(L->launch(f, d, b_end, t_beg, s.s_main));
+    FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_bnd_done, 0));
+    FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
+  }
+  return FDB_OK;
+}
+
+// ---- reductions -------------------------------------------------------------------------
+static int field_reduce(Field* f, int p, int mode, double mean, double* out) {
+  const int64_t plane = f->geo.plane();
+  const int64_t n0 = f->geo.n[0];
+  std::vector<double> sums((size_t)n0, 0.0);
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_TRY(launch_plane_sums(f->body(d, p), s.nloc(), plane, mode, mean, s.partial, s.plane_sums,
+                              s.s_main));
+  }
+  if (f->comm && f->comm->nranks > 1) {
+    fdb_comm* c = f->comm;
+    Slab& s = f->slabs[0];
+    if (c->scratch_doubles < (size_t)n0) {
+      if (c->scratch) FDB_CUDA(cudaFree(c->scratch));
+      FDB_CUDA(cudaMalloc(&c->scratch, (size_t)n0 * sizeof(double)));
+      c->scratch_doubles = (size_t)n0;
+    }
+    FDB_NCCL(ncclAllGather(s.plane_sums, c->scratch, (size_t)s.nloc(), ncclDouble, c->nccl, s.s_main));
+    count_launch();
+    FDB_CUDA(cudaMemcpyAsync(sums.data(), c->scratch, (size_t)n0 * sizeof(double),
+                             cudaMemcpyDeviceToHost, s.s_main));
+    FDB_CUDA(cudaStreamSynchronize(s.s_main));
+  } else {
+    for (int d = 0; d < f->ngpus; ++d) {
+      Slab& s = f->slabs[d];
+      FDB_CUDA(cudaSetDevice(s.device));
+      FDB_CUDA(cudaMemcpyAsync(sums.data() + s.lo, s.plane_sums, (size_t)s.nloc() * sizeof(double),
+                               cudaMemcpyDeviceToHost, s.s_main));
+    }
+    for (auto& s : f->slabs) {
+      FDB_CUDA(cudaSetDevice(s.device));
+      FDB_CUDA(cudaStreamSynchronize(s.s_main));
+    }
+  }
+  double acc = 0.0;
+  for (int64_t i = 0; i < n0; ++i) acc += sums[(size_t)i];  // global plane order
+  *out = acc;
+  return FDB_OK;
+}
+
+int field_sum(Field* f, int p, double* out) { return field_reduce(f, p, 0, 0.0, out); }
+int field_sqdev(Field* f, int p, double mean, double* out) { return field_reduce(f, p, 1, mean, out); }
+
+}  // namespace fdb

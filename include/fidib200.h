@@ -1,0 +1,183 @@
+/*
+ * fidib200.h -- C ABI of the B200-native FiDiBench finite-difference engines.
+ *
+ * This is the drop-in boundary: the reference (pletzer/fidibench) has no FFI
+ * layer, its engines are two C++ classes that each driver constructs directly,
+ * so the ABI below is the public surface of those classes restated with plain
+ * pointers and sizes.  "ref:" citations are relative to the reference tree.
+ *
+ *   fdb_upwind_*   <->  template<size_t NDIMS> class Upwind   ref: upwind/cxx/upwind.cxx:19-135
+ *   fdb_stencil_*  <->  class Filter                          ref: cxx/Filter.h:36-170, cxx/Filter.cpp
+ *   fdb_comm_*, fdb_slab_partition  <->  MPI_COMM_WORLD + CubeDecomp   ref: cxx/CubeDecomp.cpp:11-131
+ *
+ * Conventions
+ *   - every entry point returns 0 (FDB_OK) or a negative FDB_E_* code; the text
+ *     of the last failure on the calling thread is fdb_last_error().  No C++
+ *     exception crosses this boundary.
+ *   - there is no CPU fallback: without a usable CUDA device every create call
+ *     fails with FDB_E_CUDA.
+ *   - fields are FP64.  Host fields are row-major (last axis fastest, as
+ *     upwind.cxx:39-44) unless a layout argument says FDB_COL_MAJOR (first axis
+ *     fastest, Filter's local storage, Filter.cpp:50).
+ *   - a handle owns all device memory, streams and events it needs; host
+ *     buffers are caller-owned and only touched during the call.
+ *   - a handle is driven by one caller thread at a time.  Calls are synchronous
+ *     at return unless the name ends in _async.
+ *   - domains are periodic in every axis and partitioned in slabs along axis 0.
+ *     Two ways to use several GPUs:
+ *       (1) one process, `ngpus` devices 0..ngpus-1 (peer-to-peer halo stores);
+ *       (2) one process per GPU: each rank builds an fdb_comm (NCCL over
+ *           NVLink) and creates its engines with the *_dist constructors; it
+ *           then owns planes [lo,hi) of axis 0 only.
+ */
+#ifndef FIDIB200_H
+#define FIDIB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDB_VERSION_MAJOR 0
+#define FDB_VERSION_MINOR 1
+
+/* ---- status ------------------------------------------------------------ */
+enum {
+  FDB_OK = 0,
+  FDB_E_INVALID = -1, /* bad argument                                            */
+  FDB_E_CUDA = -2,    /* CUDA runtime/driver failure, or no device               */
+  FDB_E_NCCL = -3,    /* NCCL failure                                            */
+  FDB_E_OOM = -4,     /* device or host allocation failed                        */
+  FDB_E_DECOMP = -5,  /* no valid slab decomposition (ref: Filter.cpp:27-34)     */
+  FDB_E_STATE = -6    /* call not valid in the handle's current state            */
+};
+enum { FDB_ROW_MAJOR = 0, FDB_COL_MAJOR = 1 };
+enum { FDB_INPUT = 0, FDB_OUTPUT = 1 }; /* ref: Filter::computeCheckSum("input"|"output") */
+
+/* kernel selection for fdb_upwind_set_kernel / fdb_stencil_set_kernel */
+enum {
+  FDB_KERNEL_AUTO = 0,    /* fastest kernel that supports the problem            */
+  FDB_KERNEL_GENERIC = 1, /* one-thread-per-cell global-memory kernel, any shape */
+  FDB_KERNEL_TMA = 2      /* TMA-staged shared-memory tile pipeline (3-D)        */
+};
+
+const char *fdb_last_error(void);
+int fdb_version(int *major, int *minor);
+int fdb_device_count(int *count);
+/* number of CUDA kernels this library has launched in this process so far */
+int fdb_launch_count(int64_t *count);
+
+/* ---- partition: replaces CubeDecomp (ref: cxx/CubeDecomp.cpp:88-109) ----- */
+/* planes [lo,hi) of axis 0 owned by `part` of `nparts`; FDB_E_DECOMP unless
+ * nparts divides n0 (the reference has the same requirement, CubeDecomp.cpp:26-28). */
+int fdb_slab_partition(int64_t n0, int nparts, int part, int64_t *lo, int64_t *hi);
+
+/* ---- communicator for one-process-per-GPU runs --------------------------- */
+typedef struct fdb_comm fdb_comm;
+#define FDB_COMM_ID_BYTES 128
+/* rank 0 calls this and ships the 128 bytes to every rank (any transport) */
+int fdb_comm_unique_id(void *id_bytes);
+/* collective over all ranks; `device` is the CUDA device this rank drives */
+int fdb_comm_create(int rank, int nranks, const void *id_bytes, int device, fdb_comm **out);
+int fdb_comm_rank(const fdb_comm *c, int *rank, int *nranks);
+int fdb_comm_barrier(fdb_comm *c);
+/* max over ranks of a host double (timing), collective */
+int fdb_comm_max(fdb_comm *c, double *value);
+int fdb_comm_destroy(fdb_comm *c);
+
+/* ---- Upwind engine -------------------------------------------------------- */
+typedef struct fdb_upwind fdb_upwind;
+
+/* ref: Upwind<NDIMS>::Upwind(velocity, lengths, numCells), upwind.cxx:23-49.
+ * ndims in 1..3.  The field starts as the ctor's: all zero, cell 0 = 1.
+ * ngpus >= 1 devices of this process; must divide numCells[0]. */
+int fdb_upwind_create(int ndims, const int64_t *numCells, const double *velocity,
+                      const double *lengths, int ngpus, fdb_upwind **out);
+/* same engine, this process owning one slab of the comm's ranks */
+int fdb_upwind_create_dist(int ndims, const int64_t *numCells, const double *velocity,
+                           const double *lengths, fdb_comm *comm, fdb_upwind **out);
+/* planes [lo,hi) of axis 0 held by this handle (whole domain when not dist) */
+int fdb_upwind_local_range(const fdb_upwind *h, int64_t *lo, int64_t *hi);
+
+/* overwrite the field from a host array holding the WHOLE domain (row-major);
+ * in dist mode each rank takes its own planes out of it */
+int fdb_upwind_set_field(fdb_upwind *h, const double *host_field);
+/* overwrite only this handle's planes [lo,hi) from a host array of that size */
+int fdb_upwind_set_slab(fdb_upwind *h, const double *host_slab);
+/* reset to the ctor's initial condition (delta at cell 0), upwind.cxx:45-48 */
+int fdb_upwind_reset(fdb_upwind *h);
+
+/* ref: Upwind::advect(numTimeSteps, deltaTime), upwind.cxx:51-86 */
+int fdb_upwind_advect(fdb_upwind *h, int64_t numTimeSteps, double deltaTime);
+/* enqueue only; pair with fdb_upwind_sync */
+int fdb_upwind_advect_async(fdb_upwind *h, int64_t numTimeSteps, double deltaTime);
+int fdb_upwind_sync(fdb_upwind *h);
+/* ref: main()'s dt = min_j 0.1*dx_j/v_j, upwind.cxx:186-192 */
+int fdb_upwind_default_dt(const fdb_upwind *h, double *dt);
+
+/* ref: Upwind::checksum(), upwind.cxx:91-93 (collective in dist mode; every rank gets the sum) */
+int fdb_upwind_checksum(fdb_upwind *h, double *sum);
+/* ref: Upwind::std(), upwind.cxx:95-103 */
+int fdb_upwind_std(fdb_upwind *h, double *stddev);
+/* whole-domain copy-out, row-major (feeds the host-side saveVTK/print);
+ * in dist mode only planes [lo,hi) of host_field are written */
+int fdb_upwind_get_field(fdb_upwind *h, double *host_field);
+int fdb_upwind_get_slab(fdb_upwind *h, double *host_slab);
+
+/* FDB_KERNEL_*; FDB_E_INVALID if the kernel cannot run this problem */
+int fdb_upwind_set_kernel(fdb_upwind *h, int kernel);
+/* which kernel the next advect will use (FDB_KERNEL_GENERIC or FDB_KERNEL_TMA) */
+int fdb_upwind_get_kernel(const fdb_upwind *h, int *kernel);
+/* time steps fused per sweep by the TMA kernel (temporal blocking), >= 1 */
+int fdb_upwind_set_fuse(fdb_upwind *h, int steps_per_sweep);
+/* run the handle's work on a caller-owned cudaStream_t (NULL = the handle's own) */
+int fdb_upwind_set_stream(fdb_upwind *h, void *cuda_stream);
+/* device time of the last advect (CUDA events on the handle's stream, max over
+ * this process's devices), cell-updates done, and halo bytes sent per device */
+int fdb_upwind_last_timing(const fdb_upwind *h, double *gpu_ms, double *cell_updates,
+                           double *halo_bytes);
+int fdb_upwind_destroy(fdb_upwind *h);
+
+/* ---- generic stencil engine (Filter) -------------------------------------- */
+typedef struct fdb_stencil fdb_stencil;
+
+/* ref: Filter::Filter(globalDims, xmins, xmaxs, stencil), Filter.cpp:11-78.
+ * offsets is nbranch x ndims (row-major), weights nbranch; the branches are
+ * applied in std::map order (lexicographic on the offset vector,
+ * Filter.cpp:202) whatever order they are passed in; duplicates are rejected.
+ * out = sum_b w_b * in[(idx + offset_b) mod dims], accumulated from 0.0 with a
+ * separately rounded multiply and add per branch, exactly as Filter.cpp:247-251.
+ * ngpus must divide globalDims[0]. */
+int fdb_stencil_create(int ndims, const int64_t *globalDims, int nbranch, const int *offsets,
+                       const double *weights, int ngpus, fdb_stencil **out);
+int fdb_stencil_create_dist(int ndims, const int64_t *globalDims, int nbranch, const int *offsets,
+                            const double *weights, fdb_comm *comm, fdb_stencil **out);
+int fdb_stencil_local_range(const fdb_stencil *h, int64_t *lo, int64_t *hi);
+/* ref: Filter::setInData / setInDataByIndices (Filter.cpp:131-188): the driver
+ * evaluates its callback on the host and hands the array over (whole domain) */
+int fdb_stencil_set_input(fdb_stencil *h, const double *host_field, int layout);
+int fdb_stencil_set_input_slab(fdb_stencil *h, const double *host_slab);
+/* ref: Filter::applyFilter(), Filter.cpp:191-263 */
+int fdb_stencil_apply(fdb_stencil *h);
+/* ref: Filter::copyOutToIn(), Filter.cpp:440-463 -- O(1): the buffers swap
+ * roles and "output" keeps reading as the same data until the next apply */
+int fdb_stencil_swap(fdb_stencil *h);
+/* niter x { apply; swap } as laplacian.cxx:86-90, enqueued back to back */
+int fdb_stencil_iterate(fdb_stencil *h, int64_t niter);
+/* ref: Filter::computeCheckSum("input"|"output"), Filter.cpp:465-485 */
+int fdb_stencil_checksum(fdb_stencil *h, int which, double *sum);
+int fdb_stencil_get(fdb_stencil *h, int which, double *host_field, int layout);
+int fdb_stencil_get_slab(fdb_stencil *h, int which, double *host_slab);
+int fdb_stencil_set_kernel(fdb_stencil *h, int kernel);
+int fdb_stencil_get_kernel(const fdb_stencil *h, int *kernel);
+int fdb_stencil_set_stream(fdb_stencil *h, void *cuda_stream);
+int fdb_stencil_last_timing(const fdb_stencil *h, double *gpu_ms, double *cell_updates,
+                            double *halo_bytes);
+int fdb_stencil_destroy(fdb_stencil *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIDIB200_H */

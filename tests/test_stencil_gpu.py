@@ -1,0 +1,123 @@
+"""Parity of the CUDA stencil engine (Filter) with the oracle / reference goldens."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden, SEED
+
+pytestmark = pytest.mark.gpu
+C = oracle.c
+
+
+def as_dict(off, w):
+    return {tuple(int(x) for x in o): float(v) for o, v in zip(off, w)}
+
+
+def test_laplacian_driver_sequence_matches_reference_golden(gpu_fb):
+    g = golden("laplacian_16.npz")
+    off, w = oracle.laplacian_stencil(3)
+    import math
+    with gpu_fb.Filter([16] * 3, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        assert fl.isDecompValid() and fl.getRank() == 0 and fl.getNumProcs() == 1
+        # ref: laplacian.cxx:22-28, evaluated on the host exactly as the driver does
+        fl.setInData(lambda pos: math.prod([math.sin(2.0 * math.pi * p) for p in pos]))
+        assert np.array_equal(fl.get(gpu_fb.FDB_INPUT), g["input"])
+        fl.applyFilter()
+        assert np.array_equal(fl.get(gpu_fb.FDB_OUTPUT), g["out1"])
+        assert np.array_equal(fl.get(gpu_fb.FDB_INPUT), g["input"])
+        fl.copyOutToIn()
+        # after copyOutToIn input == output == the applied field
+        assert np.array_equal(fl.get(gpu_fb.FDB_INPUT), g["out1"])
+        assert np.array_equal(fl.get(gpu_fb.FDB_OUTPUT), g["out1"])
+        fl.iterate(9)
+        assert np.array_equal(fl.get(gpu_fb.FDB_OUTPUT), g["out10"])  # bit-exact, H1
+        assert abs(fl.computeCheckSum("input") - float(g["sums10"][0])) < 1e-12
+        assert abs(fl.computeCheckSum("output") - float(g["sums10"][1])) < 1e-12
+
+
+def test_laplacian_2d_and_test_stencil2d(gpu_fb):
+    g = golden("laplacian2d_32.npz")
+    off, w = oracle.laplacian_stencil(2)
+    with gpu_fb.Filter([32, 32], [0.0] * 2, [1.0] * 2, as_dict(off, w)) as fl:
+        fl.set_input(g["input"])
+        fl.applyFilter()
+        assert np.array_equal(fl.get(), g["out1"])
+    t = golden("stencil2d_8.npz")
+    with gpu_fb.Filter([8, 8], [0.0] * 2, [1.0] * 2, as_dict(t["offsets"], t["weights"])) as fl:
+        fl.set_input(t["init"])
+        fl.applyFilter()
+        assert np.array_equal(fl.get(), t["out"])
+
+
+def test_upwindmpi_stencil(gpu_fb):
+    g = golden("upwindmpi_16.npz")
+    with gpu_fb.Filter([16] * 3, [0.0] * 3, [1.0] * 3, as_dict(g["offsets"], g["weights"])) as fl:
+        fl.set_input(g["init"])
+        for i in range(3):
+            fl.applyFilter()
+            fl.copyOutToIn()
+        assert np.array_equal(fl.get(), g["out3"])
+
+
+@pytest.mark.parametrize("shape", [(12, 10, 14), (20, 6), (33,), (7, 5, 3)])
+def test_generic_stencil_true_periodic_wrap_any_extent(gpu_fb, shape):
+    rng = np.random.default_rng(SEED)
+    nd = len(shape)
+    a = rng.random(shape)
+    offs = {tuple([0] * nd): -1.5}
+    for j in range(nd):
+        for s, wt in ((1, 0.25), (-1, 0.75), (2, -0.125)):
+            o = [0] * nd
+            o[j] = s
+            offs[tuple(o)] = wt
+    if nd > 1:
+        offs[tuple([1] * nd)] = 0.3  # a diagonal branch
+        offs[tuple([-1] * nd)] = -0.2
+    with gpu_fb.Filter(shape, [0.0] * nd, [1.0] * nd, offs) as fl:
+        fl.set_input(a)
+        fl.applyFilter()
+        out = fl.get()
+    ref = C.stencil_apply(a, np.array(list(offs.keys()), dtype=np.int32), np.array(list(offs.values())))
+    assert np.array_equal(out, ref)
+
+
+def test_column_major_io(gpu_fb):
+    rng = np.random.default_rng(SEED + 1)
+    a = rng.random((6, 10, 12))
+    off, w = oracle.laplacian_stencil(3)
+    with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        fl.set_input(np.asfortranarray(a).reshape(-1, order="F"), layout=gpu_fb.FDB_COL_MAJOR)
+        assert np.array_equal(fl.get(gpu_fb.FDB_INPUT), a)
+        fl.applyFilter()
+        ref = C.stencil_apply(a, off, w)
+        assert np.array_equal(fl.get(), ref)
+        col = fl.get(gpu_fb.FDB_OUTPUT, layout=gpu_fb.FDB_COL_MAJOR)
+        assert np.array_equal(col.reshape(-1).reshape(a.shape, order="F"), ref)
+
+
+def test_duplicate_or_empty_stencils_rejected(gpu_fb):
+    import ctypes as Ct
+    from fidibench_b200 import _lib
+    h = Ct.c_void_p()
+    offs = np.array([[0, 0], [0, 0]], dtype=np.int32)
+    w = np.array([1.0, 2.0])
+    rc = _lib.lib.fdb_stencil_create(2, _lib.arr_i64([8, 8]), 2, offs.ctypes.data_as(_lib.p_i32),
+                                     w.ctypes.data_as(_lib.p_dbl), 1, Ct.byref(h))
+    assert rc == -1 and b"duplicate" in _lib.lib.fdb_last_error()
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_in_process_slabs_two_sided_halo(gpu_fb, ngpus):
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(SEED + 2)
+    a = rng.random((16, 12, 32))
+    off, w = oracle.laplacian_stencil(3)
+    with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(off, w), ngpus=ngpus) as fl:
+        fl.set_input(a)
+        fl.iterate(6)
+        out = fl.get()
+    ref = a
+    for _ in range(6):
+        ref = C.stencil_apply(ref, off, w)
+    assert np.array_equal(out, ref)

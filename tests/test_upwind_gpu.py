@@ -1,0 +1,205 @@
+"""Parity of the CUDA upwind engine (through the C ABI) with the oracle and the
+golden fixtures.  Bit-exact on the field; 1e-12 relative on checksum/std (the
+reference sums sequentially, SURVEY.md H4 -- tolerance from north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden, SEED
+
+pytestmark = pytest.mark.gpu
+C = oracle.c
+RTOL = 1e-12  # north_star: "global checksum and the full field agree within 1e-12 relative"
+
+
+def run_gpu(fb, init, steps, velocity=None, lengths=None, dt=None, kernel=None, ngpus=1):
+    shape = init.shape
+    nd = len(shape)
+    velocity = [1.0] * nd if velocity is None else list(velocity)
+    lengths = [1.0] * nd if lengths is None else list(lengths)
+    with fb.Upwind(velocity, lengths, shape, ngpus=ngpus) as up:
+        if kernel is not None:
+            up.set_kernel(kernel)
+        up.set_field(init)
+        if dt is None:
+            dt = up.default_dt()
+        up.advect(steps, dt)
+        return up.field(), up.checksum(), up.std(), up.kernel()
+
+
+def delta(shape):
+    f = np.zeros(shape)
+    f.reshape(-1)[0] = 1.0
+    return f
+
+
+def test_config1_128cubed_10_steps_matches_reference_golden(gpu_fb):
+    g = golden("upwind_128_s10.npz")
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [128] * 3) as up:  # ctor state = delta at cell 0
+        assert up.default_dt() == float(g["dt"])
+        assert up.kernel() == gpu_fb.FDB_KERNEL_TMA
+        up.advect(10, up.default_dt())
+        f = up.field()
+        assert np.array_equal(f[:11, :11, :11], g["corner"])
+        assert np.count_nonzero(f) == 286
+        assert up.checksum() == pytest.approx(float(g["checksum"]), rel=RTOL)
+        assert up.std() == pytest.approx(float(g["std"]), rel=RTOL)
+        assert f"{up.checksum():g}" == "1"  # the reference's ctest regex "check sum: 1"
+    ref = C.upwind_advect(delta((128,) * 3), 10)
+    assert np.array_equal(f, ref)
+
+
+@pytest.mark.parametrize("kernel", ["generic", "tma"])
+@pytest.mark.parametrize("shape,steps", [((16, 16, 16), 100), ((64, 64, 64), 5), ((24, 20, 28), 7),
+                                         ((96, 64, 128), 3), ((8, 34, 130), 4), ((5, 3, 6), 9),
+                                         ((32, 16, 256), 3), ((3, 40, 260), 2)])
+def test_random_field_bitwise_vs_oracle(gpu_fb, kernel, shape, steps):
+    rng = np.random.default_rng(SEED)
+    a = rng.random(shape)
+    k = gpu_fb.FDB_KERNEL_GENERIC if kernel == "generic" else gpu_fb.FDB_KERNEL_TMA
+    f, cs, sd, used = run_gpu(gpu_fb, a, steps, kernel=k)
+    assert used == k
+    ref = C.upwind_advect(a, steps)
+    assert np.array_equal(f, ref)
+    assert cs == pytest.approx(C.checksum(ref), rel=RTOL)
+    assert sd == pytest.approx(C.std(ref), rel=RTOL)
+
+
+@pytest.mark.parametrize("case", ["pos", "mixed", "neg"])
+def test_random_field_golden_from_reference(gpu_fb, case):
+    g = golden("upwind_random_24x20x28.npz")
+    f, cs, sd, _ = run_gpu(gpu_fb, g["init"], int(g[f"{case}_steps"]), velocity=g[f"{case}_vel"],
+                           lengths=g[f"{case}_len"], dt=float(g[f"{case}_dt"]))
+    assert np.array_equal(f, g[f"{case}_out"])
+    assert cs == pytest.approx(float(g[f"{case}_checksum"]), rel=RTOL)
+    assert sd == pytest.approx(float(g[f"{case}_std"]), rel=RTOL)
+
+
+def test_mass_wraps_around_many_times(gpu_fb):
+    g = golden("upwind_16_s100.npz")
+    for k in (gpu_fb.FDB_KERNEL_GENERIC, gpu_fb.FDB_KERNEL_TMA):
+        f, cs, _, _ = run_gpu(gpu_fb, delta((16,) * 3), 100, kernel=k)
+        assert np.array_equal(f, g["out"])
+        assert cs == pytest.approx(float(g["checksum"]), rel=RTOL)
+
+
+def test_1d_and_2d_instantiations(gpu_fb):
+    g = golden("upwind_1d2d.npz")
+    f1, _, _, k1 = run_gpu(gpu_fb, g["init1"], 5)
+    f2, _, _, k2 = run_gpu(gpu_fb, g["init2"], 5)
+    assert np.array_equal(f1, g["out1"]) and np.array_equal(f2, g["out2"])
+    assert k1 == k2 == gpu_fb.FDB_KERNEL_GENERIC
+
+
+def test_negative_and_zero_velocities(gpu_fb):
+    rng = np.random.default_rng(SEED + 3)
+    a = rng.random((12, 18, 20))
+    for vel in ([-1, 2, 0.5], [1, 1, -1], [0.0, 1, 1]):
+        f, _, _, _ = run_gpu(gpu_fb, a, 6, velocity=vel, lengths=[1, 2, 1], dt=0.004)
+        assert np.array_equal(f, C.upwind_advect(a, 6, velocity=vel, lengths=[1, 2, 1], dt=0.004))
+
+
+def test_tma_kernel_rejects_what_it_cannot_run(gpu_fb):
+    with gpu_fb.Upwind([1.0, -1.0, 1.0], [1.0] * 3, [8, 8, 8]) as up:
+        assert up.kernel() == gpu_fb.FDB_KERNEL_GENERIC
+        with pytest.raises(gpu_fb.FdbError):
+            up.set_kernel(gpu_fb.FDB_KERNEL_TMA)
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [8, 8, 9]) as up:  # odd rows are not 16-byte pitched
+        assert up.kernel() == gpu_fb.FDB_KERNEL_GENERIC
+
+
+def test_repeated_advect_calls_equal_one_call(gpu_fb):
+    rng = np.random.default_rng(SEED + 4)
+    a = rng.random((32, 32, 64))
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as up:
+        up.set_field(a)
+        dt = up.default_dt()
+        for n in (1, 2, 3):
+            up.advect(n, dt)
+        assert np.array_equal(up.field(), C.upwind_advect(a, 6))
+        up.reset()
+        up.advect(4, dt)
+        assert np.array_equal(up.field(), C.upwind_advect(delta(a.shape), 4))
+        t = up.last_timing()
+        assert t["gpu_ms"] > 0 and t["cell_updates"] == 4 * a.size
+
+
+def test_config2_512cubed_100_steps_corner_rule(gpu_fb):
+    """BASELINE config 2 at full size.  S=100 < 128, so the non-zero corner is
+    bit-identical to the reference's 128^3 x 100 run and every other
+    cell is exactly zero; mass is conserved."""
+    g = golden("upwind_128_s100.npz")
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [512] * 3) as up:
+        assert up.kernel() == gpu_fb.FDB_KERNEL_TMA
+        up.advect(100, up.default_dt())
+        f = up.field()
+        cs, sd = up.checksum(), up.std()
+    assert np.array_equal(f[:101, :101, :101], g["corner"])
+    assert np.count_nonzero(f) == int(g["nnz"])
+    assert cs == pytest.approx(float(g["checksum"]), rel=RTOL)
+    assert cs == pytest.approx(1.0, rel=RTOL)
+    # std depends on N: sqrt(sum((f-mean)^2)/N^3), recomputed on the host from the field
+    mean = cs / f.size
+    assert sd == pytest.approx(float(np.sqrt(np.sum((f - mean) ** 2) / f.size)), rel=1e-10)
+
+
+def test_linearity_at_full_plane_size(gpu_fb):
+    """Size-independent property: the step is linear, A(x + 2y) == A(x) + 2 A(y) to rounding."""
+    rng = np.random.default_rng(SEED + 5)
+    shape = (8, 256, 512)
+    x, y = rng.random(shape), rng.random(shape)
+    fx = run_gpu(gpu_fb, x, 3)[0]
+    fy = run_gpu(gpu_fb, y, 3)[0]
+    fxy = run_gpu(gpu_fb, x + 2 * y, 3)[0]
+    assert np.allclose(fxy, fx + 2 * fy, rtol=1e-13, atol=0)
+
+
+def test_caller_stream(gpu_fb):
+    import torch
+    rng = np.random.default_rng(SEED + 6)
+    a = rng.random((16, 32, 64))
+    s = torch.cuda.Stream()
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as up:
+        up.set_stream(s.cuda_stream)
+        up.set_field(a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s):
+            e0.record()
+            up.advect_async(5, up.default_dt())
+            e1.record()
+        up.sync()
+        s.synchronize()
+        assert e0.elapsed_time(e1) > 0
+        assert np.array_equal(up.field(), C.upwind_advect(a, 5))
+        up.set_stream(None)
+
+
+def test_launch_counter_moves(gpu_fb):
+    before = gpu_fb.launch_count()
+    run_gpu(gpu_fb, delta((16, 16, 16)), 3)
+    assert gpu_fb.launch_count() >= before + 3
+
+
+@pytest.mark.parametrize("ngpus", [2, 4, 8])
+@pytest.mark.parametrize("kernel", ["generic", "tma"])
+def test_in_process_slabs_match_single_domain_oracle(gpu_fb, ngpus, kernel):
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(SEED + 7)
+    a = rng.random((16, 24, 64))
+    k = gpu_fb.FDB_KERNEL_GENERIC if kernel == "generic" else gpu_fb.FDB_KERNEL_TMA
+    f, cs, _, _ = run_gpu(gpu_fb, a, 20, kernel=k, ngpus=ngpus)
+    ref = C.upwind_advect(a, 20)
+    assert np.array_equal(f, ref)
+    f1, cs1, _, _ = run_gpu(gpu_fb, a, 20, kernel=k, ngpus=1)
+    assert cs == cs1  # the reduction is bitwise partition-invariant
+    # negative axis-0 velocity: the ghost plane sits above the slab
+    f, _, _, _ = run_gpu(gpu_fb, a, 9, velocity=[-1, 1, 1], ngpus=ngpus)
+    assert np.array_equal(f, C.upwind_advect(a, 9, velocity=[-1, 1, 1]))
+
+
+def test_invalid_slab_count_is_a_decomposition_error(gpu_fb):
+    with pytest.raises(gpu_fb.FdbError) as e:
+        gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [9, 8, 8], ngpus=2) if gpu_fb.device_count() >= 2 else \
+            gpu_fb.slab_partition(9, 2, 0)
+    assert e.value.code == -5
