@@ -1,0 +1,40 @@
+"""Builds the C++ drivers (host code only; they link libfidib200.so through its C ABI).
+
+    python -m drivers.build      ->  drivers/bin/{upwindCuda,laplacianCuda,upwindMpiCuda}
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BIN = os.path.join(HERE, "bin")
+LIBDIR = os.path.join(ROOT, "fidibench_b200", "lib")
+TARGETS = ["upwindCuda", "laplacianCuda", "upwindMpiCuda"]
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def build(force: bool = False) -> list[str]:
+    from fidibench_b200 import build as fbuild
+    fbuild.build()
+    os.makedirs(BIN, exist_ok=True)
+    outs = []
+    headers = [os.path.join(HERE, h) for h in ("cmdline.hpp", "Upwind.hpp", "Filter.hpp")] + \
+              [os.path.join(ROOT, "include", "fidib200.h")]
+    for t in TARGETS:
+        src, out = os.path.join(HERE, t + ".cxx"), os.path.join(BIN, t)
+        outs.append(out)
+        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out)
+                                                     for d in [src] + headers):
+            continue
+        cmd = [CXX, "-std=c++11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", HERE, src,
+               "-o", out, "-L", LIBDIR, "-lfidib200", "-Wl,-rpath,$ORIGIN/../../fidibench_b200/lib",
+               "-Wl,--allow-shlib-undefined"]
+        subprocess.run(cmd, check=True)
+    return outs
+
+
+if __name__ == "__main__":
+    print("\n".join(build(force="--force" in sys.argv)))

@@ -1,0 +1,86 @@
+// laplacianCuda -- the reference's laplacian driver (ref: laplacian/cxx/laplacian.cxx:30-129)
+// on the B200 backend: -numCells (8000) -numDims (2) -vtk, 10 x { applyFilter; copyOutToIn },
+// "Laplace times min/max/avg:" and "Check sums: input = .. output = .." lines.
+// MPI ranks are replaced by the GPUs of one box (-ngpus).
+#include <chrono>
+#include <cmath>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "Filter.hpp"
+#include "cmdline.hpp"
+
+// ref: laplacian.cxx:22-28
+static double func(const std::vector<double>& pos) {
+  double res = 1;
+  for (size_t i = 0; i < pos.size(); ++i) res *= sin(2.0 * M_PI * pos[i]);
+  return res;
+}
+
+int main(int argc, char** argv) {
+  CmdLineArgParser args;
+  args.setPurpose("Purpose: benchmark finite difference operations.");
+  args.set("-numCells", 8000, "Number of cells along each axis");
+  args.set("-numDims", 2, "Number of dimensions");
+  args.set("-vtk", false, "Write output to VTK file");
+  args.set("-ngpus", 1, "Number of GPUs of this box sharing the domain (slabs along axis 0)");
+  args.set("-numIter", 10, "Number of apply/copy iterations (the reference hard-codes 10)");
+
+  const bool success = args.parse(argc, argv);
+  const bool help = args.get<bool>("-h");
+
+  if (success && !help) {
+    const size_t numCells = (size_t)args.get<int>("-numCells");
+    const size_t numDims = (size_t)args.get<int>("-numDims");
+    const bool writeVTK = args.get<bool>("-vtk");
+
+    // the stencil, ref: laplacian.cxx:55-65 (no 1/h^2 scaling)
+    std::map<std::vector<int>, double> stencil;
+    std::vector<int> offset(numDims, 0);
+    stencil[offset] = -2.0 * numDims;
+    for (size_t i = 0; i < numDims; ++i) {
+      offset[i] = 1;
+      stencil[offset] = 1.0;
+      offset[i] = -1;
+      stencil[offset] = 1.0;
+      offset[i] = 0;
+    }
+
+    std::vector<size_t> globalDims(numDims, numCells);
+    std::vector<double> xmins(numDims, 0.0), xmaxs(numDims, 1.0);
+
+    try {
+      fidib200::Filter fltr(globalDims, xmins, xmaxs, stencil, args.get<int>("-ngpus"));
+      if (!fltr.isDecompValid()) std::cerr << "Decomposition is invalid\n";
+      if (fltr.isDecompValid()) {
+        fltr.setInData(func);
+        const auto tic = std::chrono::steady_clock::now();
+        // repeat to improve statistics
+        const size_t numIter = (size_t)args.get<int>("-numIter");
+        for (size_t i = 0; i < numIter; ++i) {
+          fltr.applyFilter();
+          fltr.copyOutToIn();
+        }
+        const double walltime = std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count();
+
+        if (writeVTK) {
+          std::cout << "Data will be written to file laplacian.vtk\n";
+          fltr.saveVTK("laplacian.vtk");
+        }
+        const double inSum = fltr.computeCheckSum("input");
+        const double outSum = fltr.computeCheckSum("output");
+        std::cout << "Laplace times min/max/avg: " << walltime << '/' << walltime << '/' << walltime << " [seconds]\n";
+        std::cout << "Check sums: input = " << inSum << " output = " << outSum << '\n';
+      }
+    } catch (const std::exception& e) {
+      std::cerr << "ERROR: " << e.what() << '\n';
+      return 1;
+    }
+  } else {
+    if (!success) std::cerr << "ERROR when parsing command line arguments\n";
+    args.help();
+  }
+  return 0;
+}

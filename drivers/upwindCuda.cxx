@@ -1,0 +1,96 @@
+// upwindCuda -- the reference's upwindCxx driver (ref: upwind/cxx/upwind.cxx:139-217) on the
+// B200 backend.  Same flags (-numCells -numSteps -vtk -std -h), same stdout lines
+// ("number of cells:", "number of time steps:", "check sum:", "std      :"), same exit code;
+// new, additive options select GPUs / velocity / timing output and default to the reference.
+#include <cmath>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "Upwind.hpp"
+#include "cmdline.hpp"
+
+int main(int argc, char** argv) {
+  const int ndims = 3;
+
+  CmdLineArgParser args;
+  args.setPurpose("Purpose: benchmark finite difference operations.");
+  args.set("-numCells", 128, "Number of cells along each axis");
+  args.set("-numSteps", 10, "Number of time steps");
+  args.set("-vtk", false, "Write output to VTK file");
+  args.set("-std", false, "Print out spread of solution");
+  // additions (defaults reproduce the reference run)
+  args.set("-ngpus", 1, "Number of GPUs of this box sharing the domain (slabs along axis 0)");
+  args.set("-vx", 1.0, "Velocity along axis 0");
+  args.set("-vy", 1.0, "Velocity along axis 1");
+  args.set("-vz", 1.0, "Velocity along axis 2");
+  args.set("-kernel", std::string("auto"), "auto | tma | generic");
+  args.set("-timing", false, "Print GPU time, GCUPS and full-precision sums");
+
+  const bool success = args.parse(argc, argv);
+  const bool help = args.get<bool>("-h");
+
+  if (success && !help) {
+    const int numTimeSteps = args.get<int>("-numSteps");
+    const bool doVtk = args.get<bool>("-vtk");
+    const bool doStd = args.get<bool>("-std");
+
+    // same resolution in each direction
+    std::vector<size_t> numCells(ndims, args.get<int>("-numCells"));
+    std::cout << "number of cells: ";
+    for (size_t i = 0; i < numCells.size(); ++i) std::cout << ' ' << numCells[i];
+    std::cout << '\n';
+    std::cout << "number of time steps: " << numTimeSteps << '\n';
+
+    std::vector<double> velocity(ndims);
+    velocity[0] = args.get<double>("-vx");
+    velocity[1] = args.get<double>("-vy");
+    velocity[2] = args.get<double>("-vz");
+    std::vector<double> lengths(ndims, 1.0);
+
+    // dt from the Courant number, ref: upwind.cxx:186-192 (|v| so that a negative
+    // velocity, which the class supports, still gives a positive step)
+    const double courant = 0.1;
+    double dt = std::numeric_limits<double>::max();
+    for (size_t j = 0; j < velocity.size(); ++j) {
+      const double dx = lengths[j] / numCells[j];
+      const double val = courant * dx / std::fabs(velocity[j]);
+      dt = (val < dt ? val : dt);
+    }
+
+    try {
+      fidib200::Upwind<ndims> up(velocity, lengths, numCells, args.get<int>("-ngpus"));
+      const std::string kernel = args.get<std::string>("-kernel");
+      if (kernel == "tma") up.setKernel(FDB_KERNEL_TMA);
+      if (kernel == "generic") up.setKernel(FDB_KERNEL_GENERIC);
+      if (doVtk) up.saveVTK("up0.vtk");
+      up.advect(numTimeSteps, dt);
+      const double sum = up.checksum();
+      std::cout << "check sum: " << sum << '\n';
+      double sd = 0;
+      if (doStd) {
+        sd = up.std();
+        std::cout << "std      : " << sd << '\n';
+      }
+      if (doVtk) up.saveVTK("up1.vtk");
+      if (args.get<bool>("-timing")) {
+        const double ms = up.lastGpuMilliseconds();
+        const double updates = double(numCells[0]) * numCells[1] * numCells[2] * numTimeSteps;
+        std::cout << std::setprecision(17) << "check sum (17 digits): " << sum << '\n';
+        if (doStd) std::cout << "std (17 digits): " << sd << '\n';
+        std::cout << std::setprecision(6) << "gpu time [ms]: " << ms << "  GCUPS: " << updates / ms / 1e6
+                  << "  HBM roofline GB/s (16 B/update): " << updates * 16 / ms / 1e6 << '\n';
+      }
+    } catch (const std::exception& e) {
+      std::cerr << "ERROR: " << e.what() << '\n';
+      return 1;
+    }
+  } else {
+    // error when parsing command line arguments
+    if (!success) std::cerr << "ERROR when parsing command line arguments\n";
+    args.help();
+  }
+  return 0;
+}

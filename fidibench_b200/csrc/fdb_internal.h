@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -97,6 +98,7 @@ struct Slab {
   CUtensorMap tm_glo[2];   // the G planes below local plane 0 (ghost, or wrap for 1 device)
   CUtensorMap tm_ghi[2];   // the G planes above local plane nloc-1
   bool have_tma = false;
+  int tma_cfg = 0;         // index into the TMA kernel configuration table
 };
 
 // A field decomposed in slabs over the devices this process drives, plus the

@@ -260,32 +260,70 @@ __global__ void __launch_bounds__(C::THREADS)
   }
 }
 
-using UpCfg = UpwindCfg<16, 128, 4, 6>;
+// ---- configurations -------------------------------------------------------------
+typedef void (*UpwindTmaKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                                const CUtensorMap, const UpwindTmaArgs);
+struct UpwindTmaConfig {
+  int BJ, BK, BKH, threads, smem;
+  UpwindTmaKernel kernel;
+  const char* name;
+};
+template <class C>
+constexpr UpwindTmaConfig make_cfg(const char* name) {
+  return UpwindTmaConfig{C::BJ, C::BK, C::BKH, C::THREADS, C::SMEM_BYTES, upwind3d_tma_kernel<C>, name};
+}
+// index 0 is the default; the others exist for tuning sweeps (env FDB_TMA_CFG)
+const UpwindTmaConfig kUpCfgs[] = {
+    make_cfg<UpwindCfg<16, 128, 4, 6>>("bj16_bk128_r4_s6"),
+    make_cfg<UpwindCfg<16, 128, 4, 4>>("bj16_bk128_r4_s4"),
+    make_cfg<UpwindCfg<8, 128, 4, 8>>("bj8_bk128_r4_s8"),
+    make_cfg<UpwindCfg<32, 128, 4, 3>>("bj32_bk128_r4_s3"),
+    make_cfg<UpwindCfg<16, 128, 2, 6>>("bj16_bk128_r2_s6"),
+    make_cfg<UpwindCfg<16, 64, 4, 8>>("bj16_bk64_r4_s8"),
+    make_cfg<UpwindCfg<8, 128, 2, 8>>("bj8_bk128_r2_s8"),
+    make_cfg<UpwindCfg<16, 128, 8, 6>>("bj16_bk128_r8_s6"),
+    make_cfg<UpwindCfg<32, 128, 8, 3>>("bj32_bk128_r8_s3"),
+    make_cfg<UpwindCfg<32, 128, 4, 4>>("bj32_bk128_r4_s4"),
+    make_cfg<UpwindCfg<32, 128, 4, 6>>("bj32_bk128_r4_s6"),
+    make_cfg<UpwindCfg<64, 128, 8, 3>>("bj64_bk128_r8_s3"),
+    make_cfg<UpwindCfg<32, 128, 8, 6>>("bj32_bk128_r8_s6"),
+    make_cfg<UpwindCfg<64, 128, 16, 3>>("bj64_bk128_r16_s3"),
+    make_cfg<UpwindCfg<48, 128, 8, 4>>("bj48_bk128_r8_s4"),
+};
+constexpr int kNumUpCfgs = sizeof(kUpCfgs) / sizeof(kUpCfgs[0]);
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
 
 struct KernelAttr {
   bool done = false;
   int ctas_per_sm = 1;
   int sms = 148;
 };
-KernelAttr g_up_attr[16];  // per device
+KernelAttr g_up_attr[16][kNumUpCfgs];  // per device, per config
 
 }  // namespace
 
 // Encode every tensor map slab d needs (both ping-pong buffers).  Leaves
 // have_tma = false when the row pitch is not a multiple of 16 bytes (odd n2).
 int tma_encode_slab(Field* f, int d) {
-  using C = UpCfg;
   Slab& s = f->slabs[d];
   s.have_tma = false;
+  int ci = env_int("FDB_TMA_CFG", 0);
+  if (ci < 0 || ci >= kNumUpCfgs) ci = 0;
+  s.tma_cfg = ci;
+  const UpwindTmaConfig& C = kUpCfgs[ci];
   const int64_t n1 = f->geo.n[1], n2 = f->geo.n[2];
   if (f->geo.ndims != 3 || n2 % 2 != 0 || n2 < 4) return FDB_OK;
   FDB_CUDA(cudaSetDevice(s.device));
   for (int p = 0; p < 2; ++p) {
-    FDB_TRY(encode_tensor_map_3d(&s.tm_body[p], f->body(d, p), n2, n1, s.nloc(), C::BKH, C::BJ));
-    FDB_TRY(encode_tensor_map_3d(&s.tm_row[p], f->body(d, p), n2, n1, s.nloc(), C::BKH, 1));
-    FDB_TRY(encode_tensor_map_3d(&s.tm_col[p], f->body(d, p), n2, n1, s.nloc(), 2, C::BJ));
-    FDB_TRY(encode_tensor_map_3d(&s.tm_glo[p], f->ghost_lo(d, p), n2, n1, f->G, C::BKH, C::BJ));
-    FDB_TRY(encode_tensor_map_3d(&s.tm_ghi[p], f->ghost_hi(d, p), n2, n1, f->G, C::BKH, C::BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_body[p], f->body(d, p), n2, n1, s.nloc(), C.BKH, C.BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_row[p], f->body(d, p), n2, n1, s.nloc(), C.BKH, 1));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_col[p], f->body(d, p), n2, n1, s.nloc(), 2, C.BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_glo[p], f->ghost_lo(d, p), n2, n1, f->G, C.BKH, C.BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_ghi[p], f->ghost_hi(d, p), n2, n1, f->G, C.BKH, C.BJ));
   }
   s.have_tma = true;
   return FDB_OK;
@@ -303,15 +341,13 @@ bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k) {
 int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                       cudaStream_t s) {
   if (iend <= ibeg) return FDB_OK;
-  using C = UpCfg;
   const Slab& sl = f.slabs[d];
-  KernelAttr& at = g_up_attr[sl.device & 15];
+  const UpwindTmaConfig& C = kUpCfgs[sl.tma_cfg];
+  KernelAttr& at = g_up_attr[sl.device & 15][sl.tma_cfg];
   if (!at.done) {
-    FDB_CUDA(cudaFuncSetAttribute(upwind3d_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::SMEM_BYTES));
+    FDB_CUDA(cudaFuncSetAttribute(C.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
     int nb = 0;
-    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, upwind3d_tma_kernel<C>, C::THREADS,
-                                                           C::SMEM_BYTES));
+    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C.kernel, C.threads, C.smem));
     cudaDeviceProp prop;
     FDB_CUDA(cudaGetDeviceProperties(&prop, sl.device));
     at.ctas_per_sm = nb < 1 ? 1 : nb;
@@ -324,8 +360,8 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
   a.n2 = f.geo.n[2];
   a.ibeg = ibeg;
   a.iend = iend;
-  a.njt = (int)((a.n1 + C::BJ - 1) / C::BJ);
-  a.nkt = (int)((a.n2 + C::BK - 1) / C::BK);
+  a.njt = (int)((a.n1 + C.BJ - 1) / C.BJ);
+  a.nkt = (int)((a.n2 + C.BK - 1) / C.BK);
   a.G = f.G;
   a.c0 = k.c[0];
   a.c1 = k.c[1];
@@ -335,15 +371,18 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
   const int64_t grid_max = (int64_t)at.ctas_per_sm * at.sms;
   const int64_t tiles = (int64_t)a.njt * a.nkt;
   const int64_t planes = iend - ibeg;
-  int64_t ci = 64;
-  while (ci > 4 && tiles * ((planes + ci - 1) / ci) < 8 * grid_max) ci /= 2;
+  int64_t ci = env_int("FDB_TMA_CI", 0);
+  if (ci <= 0) {
+    ci = 64;
+    while (ci > 4 && tiles * ((planes + ci - 1) / ci) < 8 * grid_max) ci /= 2;
+  }
   if (ci > planes) ci = planes;
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
   const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
   const int p = f.cur;
-  upwind3d_tma_kernel<C><<<(unsigned)grid, C::THREADS, C::SMEM_BYTES, s>>>(
-      sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p], a);
+  C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p],
+                                                     sl.tm_glo[p], a);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;

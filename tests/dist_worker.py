@@ -1,0 +1,155 @@
+"""Worker run under `python -m torch.distributed.run` by tests/test_dist_*.py.
+
+    dist_worker.py cpu   -- gloo, no GPU: id plumbing + a host model of the slab/halo protocol
+    dist_worker.py gpu   -- nccl, one rank per GPU: the real fdb_*_create_dist engines vs the oracle
+Each rank prints one line "RANK r OK ..." on success; any assertion kills the job.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import fidibench_b200 as fb  # noqa: E402
+import oracle  # noqa: E402
+
+SEED = 20261017
+
+
+def host_model_of_the_slab_ring(rank, world):
+    """The protocol libfidib200 runs on the device (runtime.cu: field_sweep/field_exchange),
+    restated with numpy slabs and gloo send/recv: each rank owns planes [lo,hi) plus one ghost
+    plane below; per step it updates its top plane first, ships it to rank+1's ghost for the
+    NEXT step, then updates the rest.  Must equal the single-domain oracle bit for bit."""
+    n0, n1, n2, steps = 8 * world, 6, 10, 2 * 8 * world + 3  # long enough to wrap the ring
+    rng = np.random.default_rng(SEED)
+    full = rng.random((n0, n1, n2))
+    lo, hi = fb.slab_partition(n0, world, rank)
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    cur = full[lo:hi].copy()
+    ghost = full[(lo - 1) % n0].copy()
+    c = -0.1  # ((dt*v)*up)/dx for the default run, any power-of-two resolution
+
+    def update(plane, below):
+        t = plane - c * (below - plane)
+        t = t - c * (np.roll(plane, 1, axis=0) - plane)
+        t = t - c * (np.roll(plane, 1, axis=1) - plane)
+        return t
+
+    for _ in range(steps):
+        new = np.empty_like(cur)
+        new[-1] = update(cur[-1], cur[-2])                     # boundary plane first
+        send = dist.isend(torch.from_numpy(new[-1].copy()), nxt)  # its halo starts travelling
+        buf = torch.empty((n1, n2), dtype=torch.float64)
+        recv = dist.irecv(buf, prv)
+        new[0] = update(cur[0], ghost)                         # interior overlaps the exchange
+        for i in range(1, cur.shape[0] - 1):
+            new[i] = update(cur[i], cur[i - 1])
+        send.wait(); recv.wait()
+        cur, ghost = new, buf.numpy().copy()
+    # single-domain result, same operation order as upwind.cxx:64-84 (axes 0, 1, 2)
+    ref = full.copy()
+    for _ in range(steps):
+        old = ref.copy()
+        for j in range(3):
+            ref = ref - c * (np.roll(old, 1, axis=j) - old)
+    assert np.array_equal(cur, ref[lo:hi]), "host slab-ring model differs from the single-domain result"
+
+
+def cpu_main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    # 1. the NCCL id travels over whatever torch.distributed backend is up
+    ids = [fb.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ids[0])
+    assert all(g == gathered[0] and len(g) == 128 for g in gathered)
+    # 2. without a GPU the communicator must refuse loudly, never fall back
+    if fb.device_count() == 0:
+        try:
+            fb.Comm(rank, world, ids[0], 0)
+            raise AssertionError("Comm() succeeded without a CUDA device")
+        except fb.FdbError as e:
+            assert e.code == -2
+    # 3. slabs tile the axis exactly
+    ranges = [None] * world
+    dist.all_gather_object(ranges, fb.slab_partition(64, world, rank))
+    assert ranges[0][0] == 0 and ranges[-1][1] == 64
+    assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    # 4. the halo protocol itself
+    host_model_of_the_slab_ring(rank, world)
+    dist.barrier()
+    print(f"RANK {rank} OK cpu", flush=True)
+    dist.destroy_process_group()
+
+
+def gpu_main():
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    comm = fb.Comm.from_torch_distributed(device=local)
+    rng = np.random.default_rng(SEED)
+
+    # upwind, both kernels, halo ring exercised by a random field and many steps
+    a = rng.random((8 * world, 24, 64))
+    for kernel in (fb.FDB_KERNEL_GENERIC, fb.FDB_KERNEL_TMA):
+        up = fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, comm=comm)
+        up.set_kernel(kernel)
+        up.set_field(a)
+        lo, hi = up.lo, up.hi
+        up.advect(8 * world + 5, up.default_dt())
+        ref = oracle.c.upwind_advect(a, 8 * world + 5)
+        assert np.array_equal(up.slab(), ref[lo:hi]), f"rank {rank}: slab differs (kernel {kernel})"
+        cs = up.checksum()
+        with fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as single:
+            single.set_field(a)
+            single.advect(8 * world + 5, single.default_dt())
+            assert cs == single.checksum(), "checksum is not partition-invariant"
+        sd = up.std()
+        assert abs(sd - oracle.c.std(ref)) <= 1e-12 * sd
+        up.close()
+
+    # negative velocity along the slab axis: ghost plane above
+    up = fb.Upwind([-1.0, 1.0, 1.0], [1.0] * 3, a.shape, comm=comm)
+    up.set_field(a)
+    up.advect(7, 0.1 / a.shape[1])
+    assert np.array_equal(up.slab(), oracle.c.upwind_advect(a, 7, velocity=[-1, 1, 1], dt=0.1 / a.shape[1])[up.lo:up.hi])
+    up.close()
+
+    # delta on the last plane of slab 0 (SURVEY.md T1 ii)
+    d = np.zeros((4 * world, 16, 32)); d[3, 15, 31] = 1.0
+    up = fb.Upwind([1.0] * 3, [1.0] * 3, d.shape, comm=comm)
+    up.set_field(d)
+    up.advect(9, up.default_dt())
+    assert np.array_equal(up.slab(), oracle.c.upwind_advect(d, 9)[up.lo:up.hi])
+    up.close()
+
+    # Laplacian (two-sided halo)
+    off, w = oracle.laplacian_stencil(3)
+    b = rng.random((4 * world, 12, 32))
+    fl = fb.Filter(b.shape, [0.0] * 3, [1.0] * 3, {tuple(int(x) for x in o): float(v) for o, v in zip(off, w)}, comm=comm)
+    fl.set_input(b)
+    fl.iterate(5)
+    ref = b
+    for _ in range(5):
+        ref = oracle.c.stencil_apply(ref, off, w)
+    out = fl.get()
+    assert np.array_equal(out[fl.lo:fl.hi], ref[fl.lo:fl.hi]), f"rank {rank}: laplacian slab differs"
+    assert abs(fl.computeCheckSum("output") - oracle.c.checksum(ref)) < 1e-9
+    fl.close()
+
+    dist.barrier()
+    print(f"RANK {rank} OK gpu", flush=True)
+    comm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    cpu_main() if sys.argv[1] == "cpu" else gpu_main()
