@@ -112,7 +112,7 @@ int upwind_common_create(int ndims, const int64_t* numCells, const double* veloc
       if (velocity[j] < 0.) need_hi = true; else need_lo = true;
     }
   }
-  int rc = field_create(&h->field, geo, 1, need_lo, need_hi, ngpus, comm, /*want_tma=*/true);
+  int rc = field_create(&h->field, geo, 1, need_lo, need_hi, ngpus, comm, /*want_tma=*/1);
   if (rc == FDB_OK) rc = field_fill_delta(&h->field, 0);
   if (rc == FDB_OK) rc = field_sync(&h->field);
   if (rc != FDB_OK) {
@@ -175,7 +175,7 @@ int stencil_common_create(int ndims, const int64_t* dims, int nbranch, const int
     }
   }
   if (G == 0) G = 1;
-  int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/true);
+  int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/2);
   if (rc == FDB_OK) rc = field_sync(&h->field);
   if (rc != FDB_OK) {
     field_destroy(&h->field);

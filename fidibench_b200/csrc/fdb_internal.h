@@ -123,7 +123,7 @@ struct Field {
 };
 
 int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_hi, int ngpus,
-                 fdb_comm* comm, bool want_tma);
+                 fdb_comm* comm, int want_tma);  // want_tma: 0 none, 1 upwind, 2 7-point stencil
 void field_destroy(Field* f);
 int field_set_stream(Field* f, void* stream);
 int field_upload(Field* f, int p, const double* host_global, const double* host_slab);

@@ -260,6 +260,227 @@ __global__ void __launch_bounds__(C::THREADS)
   }
 }
 
+
+// ---- 7-point (3-D, radius 1, axis-aligned) stencil tile configuration -----------------
+// Tile = BJ rows x BK cells; smem rows carry 2 halo cells on each side (16-byte aligned
+// boxes): pitch BK + 4.  Two extra row slots hold rows j0-1 and j0+BJ (periodic).
+template <int BJ_, int BK_, int R_, int STAGES_>
+struct Lap7Cfg {
+  static constexpr int BJ = BJ_, BK = BK_, R = R_, STAGES = STAGES_;
+  static constexpr int BKH = BK + 4;
+  static constexpr int TX = BK / 2;
+  static constexpr int TY = BJ / R;
+  static constexpr int CONSUMERS = TX * TY;
+  static constexpr int CONSUMER_WARPS = CONSUMERS / 32;
+  static constexpr int THREADS = CONSUMERS + 32;
+  static constexpr int ROW_BYTES = BKH * 8;
+  static constexpr int ROW_SLOT = (ROW_BYTES + 127) / 128 * 128;
+  static constexpr int BODY_BYTES = BJ * ROW_BYTES;
+  static constexpr int WRAP_BYTES = BJ * 16;
+  static constexpr int TOP_OFF = 0;                       // row j0-1
+  static constexpr int BODY_OFF = ROW_SLOT;               // rows j0..j0+BJ-1
+  static constexpr int BOT_OFF = BODY_OFF + BODY_BYTES;   // row j0+BJ
+  static constexpr int WRAPL_OFF = BOT_OFF + ROW_SLOT;    // cells N2-2,N2-1 (left of k = 0)
+  static constexpr int WRAPR_OFF = WRAPL_OFF + (WRAP_BYTES + 127) / 128 * 128;  // cells 0,1
+  static constexpr int STAGE_BYTES = WRAPR_OFF + (WRAP_BYTES + 127) / 128 * 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+  static_assert(BJ % R == 0 && BK % 2 == 0 && CONSUMERS % 32 == 0, "bad tile");
+  static_assert(BODY_BYTES % 128 == 0, "TMA destination must stay 128-byte aligned");
+  static_assert(BKH <= 256 && BJ <= 256, "TMA box limit");
+};
+
+// Branch slots in the reference's application order (std::map order of the offsets,
+// ref: Filter.cpp:202): (-1,0,0) (0,-1,0) (0,0,-1) (0,0,0) (0,0,1) (0,1,0) (1,0,0)
+struct Lap7Args {
+  double* out;
+  int64_t n1, n2, nloc;
+  int64_t ibeg, iend;
+  int ci, njt, nkt;
+  int64_t nwork;
+  int G;
+  double w[7];
+  int has[7];  // branch present in the stencil map (absent branches are skipped, not added as 0)
+};
+
+// acc = 0; for each present branch in order: acc = acc + w * in[...]   (ref: Filter.cpp:247-251)
+// The last branch (i+1) arrives one plane later, so the first six are accumulated when
+// plane i is in shared memory and the sum is finished when plane i+1 lands.
+template <class C>
+__global__ void __launch_bounds__(C::THREADS)
+    lap7_tma_kernel(const __grid_constant__ CUtensorMap tm_body, const __grid_constant__ CUtensorMap tm_row,
+                    const __grid_constant__ CUtensorMap tm_col, const __grid_constant__ CUtensorMap tm_glo,
+                    const __grid_constant__ CUtensorMap tm_ghi, const Lap7Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t full = smem + C::STAGES * C::STAGE_BYTES;
+  const uint32_t empty = full + C::STAGES * 8;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    // ===================== producer warp =====================
+    if ((tid & 31) == 0) {
+      prefetch_tmap(&tm_body);
+      prefetch_tmap(&tm_row);
+      prefetch_tmap(&tm_col);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+        const int kt = (int)(w % a.nkt);
+        const int jt = (int)((w / a.nkt) % a.njt);
+        const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+        const int64_t i0 = a.ibeg + ic * a.ci;
+        const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+        const int k0 = kt * C::BK - 2;
+        const int j0 = jt * C::BJ;
+        const int jm = (j0 == 0) ? (int)a.n1 - 1 : j0 - 1;
+        const int jp = (j0 + C::BJ >= (int)a.n1) ? 0 : j0 + C::BJ;
+        const bool first_k = (kt == 0), last_k = (kt == a.nkt - 1);
+        for (int64_t i = i0 - 1; i <= i1; ++i) {
+          mbar_wait(empty + 8 * stage, phase ^ 1);
+          const uint32_t st = smem + stage * C::STAGE_BYTES;
+          const uint32_t fb = full + 8 * stage;
+          if (i == i0 - 1 || i == i1) {
+            // planes just outside the chunk: only their tile cells are needed
+            mbar_expect_tx(fb, C::BODY_BYTES);
+            if (i < 0)
+              tma_load_3d(st + C::BODY_OFF, &tm_glo, fb, k0, j0, a.G - 1);
+            else if (i >= a.nloc)
+              tma_load_3d(st + C::BODY_OFF, &tm_ghi, fb, k0, j0, 0);
+            else
+              tma_load_3d(st + C::BODY_OFF, &tm_body, fb, k0, j0, (int)i);
+          } else {
+            const uint32_t bytes = C::BODY_BYTES + 2 * C::ROW_BYTES + (first_k ? C::WRAP_BYTES : 0) +
+                                   (last_k ? C::WRAP_BYTES : 0);
+            mbar_expect_tx(fb, bytes);
+            tma_load_3d(st + C::BODY_OFF, &tm_body, fb, k0, j0, (int)i);
+            tma_load_3d(st + C::TOP_OFF, &tm_row, fb, k0, jm, (int)i);
+            tma_load_3d(st + C::BOT_OFF, &tm_row, fb, k0, jp, (int)i);
+            if (first_k) tma_load_3d(st + C::WRAPL_OFF, &tm_col, fb, (int)a.n2 - 2, j0, (int)i);
+            if (last_k) tma_load_3d(st + C::WRAPR_OFF, &tm_col, fb, 0, j0, (int)i);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  const int tx = tid % C::TX;
+  const int ty = tid / C::TX;
+  const int r0 = ty * C::R;
+  const int lane = tid & 31;
+  int stage = 0;
+  uint32_t phase = 0;
+  const uint32_t col = (2 + 2 * tx) * 8;  // byte offset of this thread's two cells in a row
+
+  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    const int kt = (int)(w % a.nkt);
+    const int jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    const int64_t k = (int64_t)kt * C::BK + 2 * tx;
+    const int64_t j = (int64_t)jt * C::BJ + r0;
+    const bool wrapl_lane = (kt == 0) && (tx == 0);
+    const bool wrapr_lane = (kt == a.nkt - 1) && (tx == C::TX - 1);
+
+    double2 below[C::R];    // plane i-1
+    double2 partial[C::R];  // first six branches of plane i-1's output (waiting for plane i)
+    {
+      mbar_wait(full + 8 * stage, phase);
+      const uint32_t st = smem + stage * C::STAGE_BYTES;
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) below[r] = lds_v2(st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES + col);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    for (int64_t i = i0; i <= i1; ++i) {
+      mbar_wait(full + 8 * stage, phase);
+      const uint32_t st = smem + stage * C::STAGE_BYTES;
+      double2 ctr[C::R];
+      if (i == i1) {
+        // plane above the chunk: finishes the last output plane
+#pragma unroll
+        for (int r = 0; r < C::R; ++r) ctr[r] = lds_v2(st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES + col);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8 * stage);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      } else {
+        double km1[C::R], kp1[C::R];
+        const uint32_t up_row = (r0 == 0) ? st + C::TOP_OFF : st + C::BODY_OFF + (r0 - 1) * C::ROW_BYTES;
+        const uint32_t dn_row =
+            (r0 + C::R == C::BJ) ? st + C::BOT_OFF : st + C::BODY_OFF + (r0 + C::R) * C::ROW_BYTES;
+        const double2 up = lds_v2(up_row + col);
+        const double2 dn = lds_v2(dn_row + col);
+#pragma unroll
+        for (int r = 0; r < C::R; ++r) {
+          const uint32_t row = st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES;
+          ctr[r] = lds_v2(row + col);
+          km1[r] = lds_f64(wrapl_lane ? st + C::WRAPL_OFF + (r0 + r) * 16 + 8 : row + col - 8);
+          kp1[r] = lds_f64(wrapr_lane ? st + C::WRAPR_OFF + (r0 + r) * 16 : row + col + 16);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8 * stage);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+
+        // finish and store plane i-1 (needs this plane's centre), then start plane i
+        if (i > i0) {
+          double* orow = a.out + ((i - 1) * a.n1 + j) * a.n2 + k;
+#pragma unroll
+          for (int r = 0; r < C::R; ++r) {
+            double x = partial[r].x, y = partial[r].y;
+            if (a.has[6]) {
+              x = __dadd_rn(x, __dmul_rn(a.w[6], ctr[r].x));
+              y = __dadd_rn(y, __dmul_rn(a.w[6], ctr[r].y));
+            }
+            st_global_v2(orow + (int64_t)r * a.n2, x, y);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < C::R; ++r) {
+          const double2 jm = (r == 0) ? up : ctr[r - 1];
+          const double2 jp = (r == C::R - 1) ? dn : ctr[r + 1];
+          double x = 0.0, y = 0.0;
+          if (a.has[0]) { x = __dadd_rn(x, __dmul_rn(a.w[0], below[r].x)); y = __dadd_rn(y, __dmul_rn(a.w[0], below[r].y)); }
+          if (a.has[1]) { x = __dadd_rn(x, __dmul_rn(a.w[1], jm.x));       y = __dadd_rn(y, __dmul_rn(a.w[1], jm.y)); }
+          if (a.has[2]) { x = __dadd_rn(x, __dmul_rn(a.w[2], km1[r]));     y = __dadd_rn(y, __dmul_rn(a.w[2], ctr[r].x)); }
+          if (a.has[3]) { x = __dadd_rn(x, __dmul_rn(a.w[3], ctr[r].x));   y = __dadd_rn(y, __dmul_rn(a.w[3], ctr[r].y)); }
+          if (a.has[4]) { x = __dadd_rn(x, __dmul_rn(a.w[4], ctr[r].y));   y = __dadd_rn(y, __dmul_rn(a.w[4], kp1[r])); }
+          if (a.has[5]) { x = __dadd_rn(x, __dmul_rn(a.w[5], jp.x));       y = __dadd_rn(y, __dmul_rn(a.w[5], jp.y)); }
+          partial[r].x = x;
+          partial[r].y = y;
+          below[r] = ctr[r];
+        }
+        continue;
+      }
+      // i == i1: finish plane i1-1
+      double* orow = a.out + ((i - 1) * a.n1 + j) * a.n2 + k;
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        double x = partial[r].x, y = partial[r].y;
+        if (a.has[6]) {
+          x = __dadd_rn(x, __dmul_rn(a.w[6], ctr[r].x));
+          y = __dadd_rn(y, __dmul_rn(a.w[6], ctr[r].y));
+        }
+        st_global_v2(orow + (int64_t)r * a.n2, x, y);
+      }
+    }
+  }
+}
+
 // ---- configurations -------------------------------------------------------------
 typedef void (*UpwindTmaKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
                                 const CUtensorMap, const UpwindTmaArgs);
@@ -272,7 +493,8 @@ template <class C>
 constexpr UpwindTmaConfig make_cfg(const char* name) {
   return UpwindTmaConfig{C::BJ, C::BK, C::BKH, C::THREADS, C::SMEM_BYTES, upwind3d_tma_kernel<C>, name};
 }
-// index 0 is the default; the others exist for tuning sweeps (env FDB_TMA_CFG)
+// kDefaultUpCfg is the default (best of the round-1 sweeps at 512^3 and 1024^3, profiles/);
+// the others exist for tuning sweeps (env FDB_TMA_CFG)
 const UpwindTmaConfig kUpCfgs[] = {
     make_cfg<UpwindCfg<16, 128, 4, 6>>("bj16_bk128_r4_s6"),
     make_cfg<UpwindCfg<16, 128, 4, 4>>("bj16_bk128_r4_s4"),
@@ -291,6 +513,7 @@ const UpwindTmaConfig kUpCfgs[] = {
     make_cfg<UpwindCfg<48, 128, 8, 4>>("bj48_bk128_r8_s4"),
 };
 constexpr int kNumUpCfgs = sizeof(kUpCfgs) / sizeof(kUpCfgs[0]);
+constexpr int kDefaultUpCfg = 3;  // bj32_bk128_r4_s3: 1 CTA/SM, 512 consumer threads, 3 x 34 KB stages
 
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -311,8 +534,8 @@ KernelAttr g_up_attr[16][kNumUpCfgs];  // per device, per config
 int tma_encode_slab(Field* f, int d) {
   Slab& s = f->slabs[d];
   s.have_tma = false;
-  int ci = env_int("FDB_TMA_CFG", 0);
-  if (ci < 0 || ci >= kNumUpCfgs) ci = 0;
+  int ci = env_int("FDB_TMA_CFG", kDefaultUpCfg);
+  if (ci < 0 || ci >= kNumUpCfgs) ci = kDefaultUpCfg;
   s.tma_cfg = ci;
   const UpwindTmaConfig& C = kUpCfgs[ci];
   const int64_t n1 = f->geo.n[1], n2 = f->geo.n[2];
@@ -373,8 +596,10 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
   const int64_t planes = iend - ibeg;
   int64_t ci = env_int("FDB_TMA_CI", 0);
   if (ci <= 0) {
+    // HBM-bound: a ragged last round costs little (the remaining CTAs still saturate DRAM),
+    // re-reading a plane per work item costs 1/ci of the reads -- favour long chunks
     ci = 64;
-    while (ci > 4 && tiles * ((planes + ci - 1) / ci) < 8 * grid_max) ci /= 2;
+    while (ci > 4 && tiles * ((planes + ci - 1) / ci) < 3 * grid_max) ci /= 2;
   }
   if (ci > planes) ci = planes;
   a.ci = (int)ci;
@@ -388,9 +613,133 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
   return FDB_OK;
 }
 
-bool stencil_lap7_supported(const Field&, const StencilBranches&) { return false; }
-int launch_stencil_lap7(const Field&, int, int64_t, int64_t, const StencilBranches&, cudaStream_t) {
-  return set_error(FDB_E_STATE, "laplacian TMA kernel not built yet");
+// ---- 7-point stencil: configs, tensor maps, launcher ---------------------------------------
+namespace {
+typedef void (*Lap7Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const CUtensorMap, const Lap7Args);
+struct Lap7Config {
+  int BJ, BK, BKH, threads, smem;
+  Lap7Kernel kernel;
+  const char* name;
+};
+template <class C>
+constexpr Lap7Config make_lap_cfg(const char* name) {
+  return Lap7Config{C::BJ, C::BK, C::BKH, C::THREADS, C::SMEM_BYTES, lap7_tma_kernel<C>, name};
+}
+const Lap7Config kLapCfgs[] = {
+    make_lap_cfg<Lap7Cfg<16, 128, 4, 5>>("bj16_bk128_r4_s5"),
+    make_lap_cfg<Lap7Cfg<32, 128, 4, 3>>("bj32_bk128_r4_s3"),
+    make_lap_cfg<Lap7Cfg<32, 128, 8, 3>>("bj32_bk128_r8_s3"),
+    make_lap_cfg<Lap7Cfg<16, 64, 4, 6>>("bj16_bk64_r4_s6"),
+    make_lap_cfg<Lap7Cfg<8, 32, 4, 6>>("bj8_bk32_r4_s6"),
+};
+constexpr int kNumLapCfgs = sizeof(kLapCfgs) / sizeof(kLapCfgs[0]);
+KernelAttr g_lap_attr[16][kNumLapCfgs];
+
+// slot of an internal-axis offset in the reference's application order, or -1
+int lap7_slot(const int* o) {
+  static const int order[7][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {1, 0, 0}};
+  for (int b = 0; b < 7; ++b)
+    if (o[0] == order[b][0] && o[1] == order[b][1] && o[2] == order[b][2]) return b;
+  return -1;
+}
+
+// the largest configured tile that divides the plane (the kernel has no ragged-tile path)
+int lap7_pick_cfg(const Field& f) {
+  const int forced = env_int("FDB_LAP_CFG", -1);
+  const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
+  for (int c = 0; c < kNumLapCfgs; ++c) {
+    if (forced >= 0 && c != forced) continue;
+    if (n1 % kLapCfgs[c].BJ == 0 && n2 % kLapCfgs[c].BK == 0) return c;
+  }
+  return -1;
+}
+}  // namespace
+
+int tma_encode_slab_lap7(Field* f, int d) {
+  Slab& s = f->slabs[d];
+  s.have_tma = false;
+  if (f->geo.ndims != 3 || f->G != 1) return FDB_OK;
+  const int c = lap7_pick_cfg(*f);
+  if (c < 0) return FDB_OK;
+  s.tma_cfg = c;
+  const Lap7Config& C = kLapCfgs[c];
+  const int64_t n1 = f->geo.n[1], n2 = f->geo.n[2];
+  FDB_CUDA(cudaSetDevice(s.device));
+  for (int p = 0; p < 2; ++p) {
+    FDB_TRY(encode_tensor_map_3d(&s.tm_body[p], f->body(d, p), n2, n1, s.nloc(), C.BKH, C.BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_row[p], f->body(d, p), n2, n1, s.nloc(), C.BKH, 1));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_col[p], f->body(d, p), n2, n1, s.nloc(), 2, C.BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_glo[p], f->ghost_lo(d, p), n2, n1, f->G, C.BKH, C.BJ));
+    FDB_TRY(encode_tensor_map_3d(&s.tm_ghi[p], f->ghost_hi(d, p), n2, n1, f->G, C.BKH, C.BJ));
+  }
+  s.have_tma = true;
+  return FDB_OK;
+}
+
+bool stencil_lap7_supported(const Field& f, const StencilBranches& b) {
+  if (f.geo.ndims != 3 || f.G != 1) return false;
+  if (f.slabs.empty() || !f.slabs[0].have_tma) return false;
+  if (b.nbranch < 1 || b.nbranch > 7) return false;
+  int seen = 0;
+  for (int i = 0; i < b.nbranch; ++i) {
+    const int slot = lap7_slot(b.off[i]);
+    if (slot < 0 || (seen >> slot) & 1) return false;
+    seen |= 1 << slot;
+  }
+  return true;
+}
+
+int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const StencilBranches& b,
+                        cudaStream_t s) {
+  if (iend <= ibeg) return FDB_OK;
+  const Slab& sl = f.slabs[d];
+  const Lap7Config& C = kLapCfgs[sl.tma_cfg];
+  KernelAttr& at = g_lap_attr[sl.device & 15][sl.tma_cfg];
+  if (!at.done) {
+    FDB_CUDA(cudaFuncSetAttribute(C.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
+    int nb = 0;
+    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C.kernel, C.threads, C.smem));
+    cudaDeviceProp prop;
+    FDB_CUDA(cudaGetDeviceProperties(&prop, sl.device));
+    at.ctas_per_sm = nb < 1 ? 1 : nb;
+    at.sms = prop.multiProcessorCount;
+    at.done = true;
+  }
+  Lap7Args a;
+  a.out = f.body(d, 1 - f.cur);
+  a.n1 = f.geo.n[1];
+  a.n2 = f.geo.n[2];
+  a.nloc = sl.nloc();
+  a.ibeg = ibeg;
+  a.iend = iend;
+  a.njt = (int)(a.n1 / C.BJ);
+  a.nkt = (int)(a.n2 / C.BK);
+  a.G = f.G;
+  for (int i = 0; i < 7; ++i) { a.w[i] = 0.0; a.has[i] = 0; }
+  for (int i = 0; i < b.nbranch; ++i) {
+    const int slot = lap7_slot(b.off[i]);
+    a.w[slot] = b.w[i];
+    a.has[slot] = 1;
+  }
+  const int64_t grid_max = (int64_t)at.ctas_per_sm * at.sms;
+  const int64_t tiles = (int64_t)a.njt * a.nkt;
+  const int64_t planes = iend - ibeg;
+  int64_t ci = env_int("FDB_TMA_CI", 0);
+  if (ci <= 0) {
+    ci = 64;
+    while (ci > 4 && tiles * ((planes + ci - 1) / ci) < 4 * grid_max) ci /= 2;
+  }
+  if (ci > planes) ci = planes;
+  a.ci = (int)ci;
+  a.nwork = tiles * ((planes + ci - 1) / ci);
+  const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  const int p = f.cur;
+  C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p],
+                                                     sl.tm_ghi[p], a);
+  count_launch();
+  FDB_CUDA(cudaGetLastError());
+  return FDB_OK;
 }
 
 }  // namespace fdb

@@ -99,10 +99,11 @@ double* Field::ghost_hi(int d, int p) const {
   return body(d, p) + slabs[d].nloc() * geo.plane();
 }
 
-int tma_encode_slab(Field* f, int d);  // kernels_tma.cu
+int tma_encode_slab(Field* f, int d);       // kernels_tma.cu (upwind box shapes)
+int tma_encode_slab_lap7(Field* f, int d);  // kernels_tma.cu (7-point stencil box shapes)
 
 int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_hi, int ngpus,
-                 fdb_comm* comm, bool want_tma) {
+                 fdb_comm* comm, int want_tma) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev < 1)
@@ -183,8 +184,9 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
       }
     }
   }
-  if (want_tma) {
-    for (int d = 0; d < f->ngpus; ++d) FDB_TRY(tma_encode_slab(f, d));
+  for (int d = 0; d < f->ngpus; ++d) {
+    if (want_tma == 1) FDB_TRY(tma_encode_slab(f, d));
+    if (want_tma == 2) FDB_TRY(tma_encode_slab_lap7(f, d));
   }
   return FDB_OK;
 }

@@ -121,3 +121,65 @@ def test_in_process_slabs_two_sided_halo(gpu_fb, ngpus):
     for _ in range(6):
         ref = C.stencil_apply(ref, off, w)
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(8, 32, 128), (5, 16, 64), (16, 64, 256), (3, 8, 32), (40, 32, 128)])
+def test_seven_point_tma_kernel_bitwise(gpu_fb, shape):
+    """The TMA fast path (3-D, radius-1 axis-aligned branches, any weights) vs the oracle."""
+    rng = np.random.default_rng(SEED + 10)
+    a = rng.random(shape)
+    off, _ = oracle.laplacian_stencil(3)
+    w = rng.standard_normal(7)
+    with gpu_fb.Filter(shape, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        assert fl.kernel() == gpu_fb.FDB_KERNEL_TMA
+        fl.set_input(a)
+        fl.iterate(4)
+        out = fl.get()
+        fl.set_kernel(gpu_fb.FDB_KERNEL_GENERIC)
+        fl.set_input(a)
+        fl.iterate(4)
+        out_generic = fl.get()
+    ref = a
+    for _ in range(4):
+        ref = C.stencil_apply(ref, off, w)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(out_generic, ref)
+
+
+def test_seven_point_tma_kernel_with_missing_branches(gpu_fb):
+    """upwindMpi's 4-branch stencil is a subset of the 7-point shape: absent branches are
+    skipped, not added as zeros."""
+    g = golden("upwindmpi_16.npz")
+    rng = np.random.default_rng(SEED + 11)
+    a = rng.random((12, 16, 64))
+    with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(g["offsets"], g["weights"])) as fl:
+        assert fl.kernel() == gpu_fb.FDB_KERNEL_TMA
+        fl.set_input(a)
+        fl.iterate(3)
+        out = fl.get()
+    ref = a
+    for _ in range(3):
+        ref = C.stencil_apply(ref, g["offsets"], g["weights"])
+    assert np.array_equal(out, ref)
+
+
+def test_laplacian_128_ten_applies_noise_dominated_still_bitwise(gpu_fb):
+    """after 10 applies at 128^3 the output is amplified roundoff; only the exact
+    operation order reproduces it.  Oracle run is a few seconds on the host."""
+    off, w = oracle.laplacian_stencil(3)
+    x = C.laplacian_input([128] * 3)
+    with gpu_fb.Filter([128] * 3, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        assert fl.kernel() == gpu_fb.FDB_KERNEL_TMA
+        fl.set_input(x)
+        fl.applyFilter()
+        y1 = fl.get()
+        fl.copyOutToIn()
+        fl.iterate(9)
+        y10 = fl.get()
+    r = C.stencil_apply(x, off, w)
+    assert np.array_equal(y1, r)
+    assert np.abs(y1).max() == 0.0072207345862560501  # SURVEY.md 8c
+    for _ in range(9):
+        r = C.stencil_apply(r, off, w)
+    assert np.array_equal(y10, r)
+    assert np.abs(y10).max() == 1.2084444224735869e-06
