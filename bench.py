@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--workload", default="upwind512")
     ap.add_argument("--tsteps", type=int, default=100, help="time steps per advect() call (= per bench step)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tma"])
+    ap.add_argument("--fuse", type=int, default=0, help="time steps per sweep (temporal blocking), 0 = library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -229,7 +230,10 @@ def main():
     up = fb.Upwind([1.0, 1.0, 1.0], lengths, dims, comm=comm)
     if args.kernel != "auto":
         up.set_kernel(fb.FDB_KERNEL_GENERIC if args.kernel == "generic" else fb.FDB_KERNEL_TMA)
-    kernel_name = "upwind3d_tma_kernel" if up.kernel() == fb.FDB_KERNEL_TMA else "upwind_generic_kernel"
+    up.set_fuse(args.fuse)
+    fuse = (args.fuse or 3) if up.kernel() == fb.FDB_KERNEL_TMA else 1
+    kernel_name = ("upwind_generic_kernel" if up.kernel() != fb.FDB_KERNEL_TMA else
+                   "upwind3d_tma_kernel" if fuse == 1 else f"upwind3d_fused_kernel<T={fuse}>")
     dt = up.default_dt()
     slab_cells = up.slab_cells()
     total_cells = float(np.prod(dims))
@@ -303,9 +307,11 @@ def main():
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = measured_peak()
-    n_kernel_launches = T * args.steps            # one sweep kernel per time step (interior) per rank
+    # one sweep kernel advances `fuse` time steps of the slab; a remainder (T % fuse) runs the
+    # single-step kernel.  achieved = algorithmic bytes of all launches / their total duration.
+    n_kernel_launches = (T // fuse + T % fuse) * args.steps
     avg_launch_ms = ms / n_kernel_launches
-    algo_bytes_per_launch = slab_cells * ALGO_BYTES_PER_UPDATE
+    algo_bytes_per_launch = slab_cells * ALGO_BYTES_PER_UPDATE * T * args.steps / n_kernel_launches
     achieved = algo_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -318,7 +324,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                "how": "16 B per cell-update x cells of one launch / (CUDA-event time of the timed region / launches)"}
+                "time_steps_per_launch": fuse, "dram_frac": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "how": "16 B per cell-update x cell-updates of one launch / (CUDA-event time of the timed region / "
+                       "launches); with temporal blocking one launch advances several time steps, so the algorithmic "
+                       "figure may exceed the copy roofline -- `traffic`/`dram_frac` are the measured DRAM bytes"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -332,7 +341,7 @@ def main():
             "data": "synthetic (uniform random FP64 field)",
             "config": {"workload": f"upwind3d {dims[0]}x{dims[1]}x{dims[2]} x{T} time steps per step",
                        "cells_per_gpu": int(slab_cells), "parallelism": f"slab{world}" if world > 1 else "single",
-                       "kernel": kernel_name,
+                       "kernel": kernel_name, "time_steps_per_sweep": fuse,
                        "l2": "inputs larger than L2 (2 ping-pong fields of %.2f GiB per GPU)" % (slab_cells * 8 / 2**30)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "halo_bytes_per_gpu": halo,

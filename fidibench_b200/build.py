@@ -19,8 +19,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libfidib200.so")
-SOURCES = ["runtime.cu", "kernels_generic.cu", "kernels_tma.cu", "capi.cu"]
-HEADERS = [os.path.join(CSRC, "fdb_internal.h"), os.path.join(ROOT, "include", "fidib200.h")]
+SOURCES = ["runtime.cu", "kernels_generic.cu", "kernels_tma.cu", "kernels_fused.cu", "capi.cu"]
+HEADERS = [os.path.join(CSRC, "fdb_internal.h"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(ROOT, "include", "fidib200.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # --fmad=false: the parity contract forbids contracting a*b+c;

@@ -17,7 +17,7 @@ struct fdb_upwind {
   double lengths[3] = {1, 1, 1};
   int64_t num_cells[3] = {1, 1, 1};
   int kernel = FDB_KERNEL_AUTO;
-  int fuse = 1;
+  int fuse = 0;  // time steps per sweep; 0 = auto (kAutoFuse when the fused kernel can run)
 };
 
 struct fdb_stencil {
@@ -34,7 +34,9 @@ namespace {
 struct UpwindSweep : SweepLauncher {
   UpwindCoeffs k;
   bool tma = false;
+  int T = 1;  // time steps per sweep (> 1: the fused temporal-blocking kernel)
   int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    if (T > 1) return launch_upwind_fused(*f, d, T, ibeg, iend, k, s);
     return tma ? launch_upwind_tma(*f, d, ibeg, iend, k, s)
                : launch_upwind_generic(*f, d, ibeg, iend, k, s);
   }
@@ -48,6 +50,8 @@ struct StencilSweep : SweepLauncher {
                 : launch_stencil_generic(*f, d, ibeg, iend, *b, s);
   }
 };
+
+constexpr int kAutoFuse = 3;  // round-1 sweeps: T=3 is the fastest bit-exact setting (profiles/)
 
 // ref: upwind.cxx:34-36,72 -- upDirection, deltas and the per-axis coefficient
 // ((deltaTime * v[j]) * upDirection[j]) / deltas[j], evaluated left to right.
@@ -112,7 +116,11 @@ int upwind_common_create(int ndims, const int64_t* numCells, const double* veloc
       if (velocity[j] < 0.) need_hi = true; else need_lo = true;
     }
   }
-  int rc = field_create(&h->field, geo, 1, need_lo, need_hi, ngpus, comm, /*want_tma=*/1);
+  // ghost depth: as many planes as the fused kernel may advance per sweep, slab permitting
+  const int nparts = comm ? comm->nranks : (ngpus > 0 ? ngpus : 1);
+  const int64_t nloc = geo.n[0] / nparts;
+  const int G = (int)std::max<int64_t>(1, std::min<int64_t>(kMaxFuse, nloc));
+  int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/1);
   if (rc == FDB_OK) rc = field_fill_delta(&h->field, 0);
   if (rc == FDB_OK) rc = field_sync(&h->field);
   if (rc != FDB_OK) {
@@ -404,8 +412,17 @@ int fdb_upwind_set_kernel(fdb_upwind* h, int kernel) {
 
 int fdb_upwind_set_fuse(fdb_upwind* h, int steps_per_sweep) {
   if (!h) return set_error(FDB_E_INVALID, "null handle");
-  if (steps_per_sweep != 1)
-    return set_error(FDB_E_INVALID, "temporal blocking (fuse > 1) is not available in this build");
+  if (steps_per_sweep < 0 || steps_per_sweep > kMaxFuse)
+    return set_error(FDB_E_INVALID, "steps per sweep must be in 1..%d, or 0 for auto (got %d)", kMaxFuse,
+                     steps_per_sweep);
+  if (steps_per_sweep > 1) {
+    UpwindCoeffs k;
+    upwind_coeffs(h, 1.0, &k);
+    if (!upwind_fused_supported(h->field, k, steps_per_sweep))
+      return set_error(FDB_E_INVALID,
+                       "the fused kernel needs what the TMA kernel needs, slabs of at least %d planes and a "
+                       "plane of at least 8 x 16 cells", steps_per_sweep);
+  }
   h->fuse = steps_per_sweep;
   return FDB_OK;
 }
@@ -427,10 +444,17 @@ int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTim
   int kern = FDB_KERNEL_GENERIC;
   FDB_TRY(fdb_upwind_get_kernel(h, &kern));
   sw.tma = (kern == FDB_KERNEL_TMA);
+  const int want = (h->fuse == 0) ? kAutoFuse : h->fuse;
+  const int fuse = (sw.tma && want > 1 && upwind_fused_supported(*f, sw.k, want)) ? want : 1;
   FDB_TRY(timing_begin(f));
-  for (int64_t s = 0; s < numTimeSteps; ++s) {
-    FDB_TRY(field_sweep(f, &sw));
+  for (int64_t done = 0; done < numTimeSteps;) {
+    const int64_t left = numTimeSteps - done;
+    int t = (int)(left < fuse ? left : fuse);
+    if (t > 1 && !upwind_fused_supported(*f, sw.k, t)) t = 1;
+    sw.T = t;
+    FDB_TRY(field_sweep(f, &sw, t));
     f->cur = 1 - f->cur;
+    done += t;
   }
   FDB_TRY(timing_end(f));
   f->last_updates = (double)numTimeSteps * (double)f->geo.total();
@@ -621,7 +645,7 @@ static int stencil_apply_async(fdb_stencil* h) {
   int kern = FDB_KERNEL_GENERIC;
   FDB_TRY(fdb_stencil_get_kernel(h, &kern));
   sw.fast = (kern == FDB_KERNEL_TMA);
-  FDB_TRY(field_sweep(f, &sw));
+  FDB_TRY(field_sweep(f, &sw, f->G));
   h->out_valid = true;
   return FDB_OK;
 }

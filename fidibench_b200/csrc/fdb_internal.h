@@ -16,6 +16,8 @@
 
 namespace fdb {
 
+constexpr int kMaxFuse = 4;  // most time steps one sweep of the fused upwind kernel advances
+
 // ---- errors -----------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);
 const char* last_error();
@@ -99,6 +101,10 @@ struct Slab {
   CUtensorMap tm_ghi[2];   // the G planes above local plane nloc-1
   bool have_tma = false;
   int tma_cfg = 0;         // index into the TMA kernel configuration table
+  // fused (temporal blocking) kernel: 8 tensor maps per buffer parity, encoded on first use
+  alignas(64) unsigned char fused_maps[2][8 * sizeof(CUtensorMap)];
+  int fused_T = 0;
+  const void* fused_cfg = nullptr;
 };
 
 // A field decomposed in slabs over the devices this process drives, plus the
@@ -133,7 +139,7 @@ int field_fill_delta(Field* f, int p);
 // the boundary streams, ev_ghost_ready[p] recorded.  `after_bnd` = wait for
 // ev_bnd_done (the planes were just produced by a boundary kernel) instead of
 // ev_local_done.
-int field_exchange(Field* f, int p, bool after_bnd);
+int field_exchange(Field* f, int p, bool after_bnd, int depth);
 int field_sync(Field* f);
 // deterministic, partition-invariant reductions: per-plane tree sums on the
 // device, then a sequential sum over planes in global order (collective in
@@ -149,7 +155,7 @@ struct SweepLauncher {
   virtual int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) = 0;
   virtual ~SweepLauncher() {}
 };
-int field_sweep(Field* f, SweepLauncher* L);
+int field_sweep(Field* f, SweepLauncher* L, int depth);  // depth = ghost planes the kernel reads/exchanges
 
 // ---- kernels ----------------------------------------------------------------
 struct UpwindCoeffs {
@@ -161,6 +167,9 @@ struct UpwindCoeffs {
 int launch_upwind_generic(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                           cudaStream_t s);
 bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k);
+bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T);
+int launch_upwind_fused(Field& f, int d, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                        cudaStream_t s);
 int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                       cudaStream_t s);
 

@@ -245,7 +245,7 @@ static int field_publish(Field* f, int p) {
     FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
   }
   f->cur = p;
-  return field_exchange(f, p, /*after_bnd=*/false);
+  return field_exchange(f, p, /*after_bnd=*/false, f->G);
 }
 
 int field_upload(Field* f, int p, const double* host_global, const double* host_slab) {
@@ -294,11 +294,12 @@ int field_fill_delta(Field* f, int p) {
 
 // Fill the ghosts of buf[p].  Pull model: the copy runs on the RECEIVING device's
 // boundary stream, so every event is recorded on the device that owns it.
-int field_exchange(Field* f, int p, bool after_bnd) {
+int field_exchange(Field* f, int p, bool after_bnd, int depth) {
   if (f->single()) return FDB_OK;  // ghosts alias the far planes of the same buffer
   const int64_t plane = f->geo.plane();
-  const size_t bytes = (size_t)f->G * (size_t)plane * sizeof(double);
-  const int64_t gcount = (int64_t)f->G * plane;
+  const size_t bytes = (size_t)depth * (size_t)plane * sizeof(double);
+  const int64_t gcount = (int64_t)depth * plane;
+  const int64_t lo_skip = (int64_t)(f->G - depth) * plane;  // the ghost planes nearest the body
   if (f->comm) {
     Slab& s = f->slabs[0];
     fdb_comm* c = f->comm;
@@ -306,12 +307,12 @@ int field_exchange(Field* f, int p, bool after_bnd) {
     // the planes to send are produced on s_bnd (after_bnd) or were published on s_main
     if (!after_bnd) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
     const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
-    double* top = f->body(0, p) + (s.nloc() - f->G) * plane;
+    double* top = f->body(0, p) + (s.nloc() - depth) * plane;
     double* bottom = f->body(0, p);
     FDB_NCCL(ncclGroupStart());
     if (f->need_lo) {
       FDB_NCCL(ncclSend(top, (size_t)gcount, ncclDouble, next, c->nccl, s.s_bnd));
-      FDB_NCCL(ncclRecv(f->ghost_lo(0, p), (size_t)gcount, ncclDouble, prev, c->nccl, s.s_bnd));
+      FDB_NCCL(ncclRecv(f->ghost_lo(0, p) + lo_skip, (size_t)gcount, ncclDouble, prev, c->nccl, s.s_bnd));
     }
     if (f->need_hi) {
       FDB_NCCL(ncclSend(bottom, (size_t)gcount, ncclDouble, prev, c->nccl, s.s_bnd));
@@ -334,8 +335,8 @@ int field_exchange(Field* f, int p, bool after_bnd) {
       const int src = (d + g - 1) % g;
       Slab& o = f->slabs[src];
       FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, after_bnd ? o.ev_bnd_done : o.ev_local_done, 0));
-      FDB_CUDA(cudaMemcpyPeerAsync(f->ghost_lo(d, p), s.device,
-                                   f->body(src, p) + (o.nloc() - f->G) * plane, o.device, bytes,
+      FDB_CUDA(cudaMemcpyPeerAsync(f->ghost_lo(d, p) + lo_skip, s.device,
+                                   f->body(src, p) + (o.nloc() - depth) * plane, o.device, bytes,
                                    s.s_bnd));
     }
     if (f->need_hi) {
@@ -352,7 +353,7 @@ int field_exchange(Field* f, int p, bool after_bnd) {
 }
 
 // One sweep: buf[cur] -> buf[1-cur] on every slab (see fdb_internal.h).
-int field_sweep(Field* f, SweepLauncher* L) {
+int field_sweep(Field* f, SweepLauncher* L, int depth) {
   const int X = f->cur, Y = 1 - X;
   if (f->single()) {
     Slab& s = f->slabs[0];
@@ -365,8 +366,8 @@ int field_sweep(Field* f, SweepLauncher* L) {
     Slab& s = f->slabs[d];
     FDB_CUDA(cudaSetDevice(s.device));
     const int64_t nloc = s.nloc();
-    const int64_t b_end = f->need_hi ? (f->G < nloc ? f->G : nloc) : 0;
-    const int64_t t_beg = f->need_lo ? (nloc - f->G > b_end ? nloc - f->G : b_end) : nloc;
+    const int64_t b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
+    const int64_t t_beg = f->need_lo ? (nloc - depth > b_end ? nloc - depth : b_end) : nloc;
     FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
     FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_ghost_ready[X], 0));
     if (!f->comm) {
@@ -382,14 +383,14 @@ int field_sweep(Field* f, SweepLauncher* L) {
     FDB_CUDA(cudaEventRecord(s.ev_bnd_done, s.s_bnd));
   }
   // 2. their halos start travelling
-  FDB_TRY(field_exchange(f, Y, /*after_bnd=*/true));
+  FDB_TRY(field_exchange(f, Y, /*after_bnd=*/true, depth));
   // 3. interior, overlapped with the exchange
   for (int d = 0; d < f->ngpus; ++d) {
     Slab& s = f->slabs[d];
     FDB_CUDA(cudaSetDevice(s.device));
     const int64_t nloc = s.nloc();
-    const int64_t b_end = f->need_hi ? (f->G < nloc ? f->G : nloc) : 0;
-    const int64_t t_beg = f->need_lo ? (nloc - f->G > b_end ? nloc - f->G : b_end) : nloc;
+    const int64_t b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
+    const int64_t t_beg = f->need_lo ? (nloc - depth > b_end ? nloc - depth : b_end) : nloc;
     FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_ghost_ready[X], 0));
     FDB_TRY(L->launch(f, d, b_end, t_beg, s.s_main));
     FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_bnd_done, 0));

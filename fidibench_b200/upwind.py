@@ -135,6 +135,10 @@ class Upwind:
         check(lib.fdb_upwind_get_kernel(self._h, C.byref(k)))
         return int(k.value)
 
+    def set_fuse(self, steps_per_sweep: int) -> None:
+        """Time steps advanced per sweep by the fused (temporal blocking) TMA kernel, 1..4."""
+        check(lib.fdb_upwind_set_fuse(self._h, int(steps_per_sweep)))
+
     def set_stream(self, cuda_stream: int | None) -> None:
         check(lib.fdb_upwind_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 

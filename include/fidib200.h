@@ -130,7 +130,8 @@ int fdb_upwind_get_slab(fdb_upwind *h, double *host_slab);
 int fdb_upwind_set_kernel(fdb_upwind *h, int kernel);
 /* which kernel the next advect will use (FDB_KERNEL_GENERIC or FDB_KERNEL_TMA) */
 int fdb_upwind_get_kernel(const fdb_upwind *h, int *kernel);
-/* time steps fused per sweep by the TMA kernel (temporal blocking), >= 1 */
+/* time steps fused per sweep by the TMA kernel (temporal blocking): 1..4, or 0 = auto
+ * (the default: the fastest setting the problem supports).  Results do not depend on it. */
 int fdb_upwind_set_fuse(fdb_upwind *h, int steps_per_sweep);
 /* run the handle's work on a caller-owned cudaStream_t (NULL = the handle's own) */
 int fdb_upwind_set_stream(fdb_upwind *h, void *cuda_stream);

@@ -1,0 +1,106 @@
+"""The C++ drivers: the reference's command lines and stdout contract (ref:
+upwind/cxx/upwind.cxx:139-217, laplacian/cxx/laplacian.cxx:30-129, upwind/cxx/upwindMpi.cxx:30-166)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import oracle
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def drivers(lib_built):
+    from drivers import build as dbuild
+    return {os.path.basename(p): p for p in dbuild.build()}
+
+
+def run(exe, *args):
+    return subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+
+
+def test_bad_option_prints_help_and_exits_zero_like_the_reference(drivers):
+    p = run(drivers["upwindCuda"], "-bogus", "3")
+    assert p.returncode == 0  # ref: upwind.cxx:207-216 returns 0 after printing help
+    assert "-bogus is not a valid option." in p.stdout
+    assert "ERROR when parsing command line arguments" in p.stderr
+    assert "Usage:" in p.stdout and "-numCells <int#> Number of cells along each axis (128)" in p.stdout
+    assert "-numSteps <int#> Number of time steps (10)" in p.stdout
+    assert "-std Print out spread of solution (0)" in p.stdout
+
+
+def test_help_flag(drivers):
+    p = run(drivers["laplacianCuda"], "-h")
+    assert p.returncode == 0
+    assert "Purpose: benchmark finite difference operations." in p.stdout
+    assert "-numCells <int#> Number of cells along each axis (8000)" in p.stdout
+    assert "-numDims <int#> Number of dimensions (2)" in p.stdout
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built on this machine")
+def test_help_text_option_lines_match_the_reference_binary(drivers):
+    ref = run(oracle.ref().upwind_exe(), "-h").stdout
+    ours = run(drivers["upwindCuda"], "-h").stdout
+    ref_opts = [l for l in ref.splitlines() if l.startswith("\t-")]
+    for line in ref_opts:  # every reference option appears verbatim (ours adds more)
+        assert line in ours.splitlines()
+
+
+@pytest.mark.gpu
+def test_upwind_driver_config1_output(drivers, gpu_fb):
+    p = run(drivers["upwindCuda"], "-numCells", "128", "-numSteps", "10", "-std", "-timing")
+    assert p.returncode == 0, p.stderr
+    out = p.stdout
+    assert "number of cells:  128 128 128\n" in out
+    assert "number of time steps: 10\n" in out
+    assert "check sum: 1\n" in out
+    assert "std      : 0.000118983\n" in out
+    assert re.search(r"[Cc]heck sum:[ ]*[1|0\.999]", out)  # the reference's ctest regex
+    m = re.search(r"check sum \(17 digits\): (\S+)", out)
+    assert abs(float(m.group(1)) - 1.0000000000000011) < 1e-12
+    # positional tokens are ignored, exactly as the reference does (it then runs 128^3)
+    p2 = run(drivers["upwindCuda"], "32", "10")
+    assert "number of cells:  128 128 128" in p2.stdout
+
+
+@pytest.mark.gpu
+def test_upwind_driver_vtk_files(drivers, gpu_fb, tmp_path):
+    p = subprocess.run([drivers["upwindCuda"], "-numCells", "8", "-numSteps", "3", "-vtk"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    up0, up1 = (tmp_path / "up0.vtk").read_text(), (tmp_path / "up1.vtk").read_text()
+    assert up0.startswith("# vtk DataFile Version 2.0\nupwind.cxx\nASCII\nDATASET RECTILINEAR_GRID\nDIMENSIONS 9 9 9\n")
+    assert "CELL_DATA 512\nSCALARS f double 1\nLOOKUP_TABLE default\n1 0 0 0 0 0 0 0 0 0 \n" in up0
+    assert "0.343 0.147 0.021 0.001 0 0 0 0 " in up1  # 0.7^3, 3*0.7^2*0.1, 3*0.7*0.01, 0.001
+    if oracle.ref_available():
+        q = subprocess.run([oracle.ref().upwind_exe(), "-numCells", "8", "-numSteps", "3", "-vtk"],
+                           cwd=tmp_path / "..", capture_output=True, text=True, env={"OMP_NUM_THREADS": "1"})
+        ref1 = (tmp_path / ".." / "up1.vtk").read_text()
+        assert ref1 == up1  # byte-identical VTK dump
+
+
+@pytest.mark.gpu
+def test_laplacian_and_upwindmpi_drivers(drivers, gpu_fb):
+    p = run(drivers["laplacianCuda"], "-numDims", "3", "-numCells", "32")
+    assert p.returncode == 0, p.stderr
+    assert "Number of procs: 1\nglobal dimensions: 32 32 32 \nDomain decomp 1 1 1 \n" in p.stdout
+    assert "Laplace times min/max/avg:" in p.stdout
+    m = re.search(r"Check sums: input = (\S+) output = (\S+)", p.stdout)
+    assert abs(float(m.group(1))) < 1e-9 and abs(float(m.group(2))) < 1e-9  # ~0 by symmetry
+    p = run(drivers["laplacianCuda"], "-numCells", "64")  # default -numDims 2
+    assert "global dimensions: 64 64 \n" in p.stdout and "Check sums:" in p.stdout
+    p = run(drivers["upwindMpiCuda"], "-numCells", "32", "-numSteps", "4")
+    assert p.returncode == 0, p.stderr
+    for i in range(4):
+        assert f"iter {i} check sum  in/out = 1 / 1\n" in p.stdout
+    assert "Check sum: 1\n" in p.stdout
+
+
+@pytest.mark.gpu
+def test_invalid_decomposition_message(drivers, gpu_fb):
+    if gpu_fb.device_count() < 2:
+        pytest.skip("needs 2 GPUs to ask for a non-dividing slab count")
+    p = run(drivers["laplacianCuda"], "-numDims", "3", "-numCells", "33", "-ngpus", "2")
+    assert "No valid domain decomposition could be found" in p.stderr
+    assert "Decomposition is invalid" in p.stderr

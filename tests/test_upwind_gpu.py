@@ -203,3 +203,59 @@ def test_invalid_slab_count_is_a_decomposition_error(gpu_fb):
         gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [9, 8, 8], ngpus=2) if gpu_fb.device_count() >= 2 else \
             gpu_fb.slab_partition(9, 2, 0)
     assert e.value.code == -5
+
+
+@pytest.mark.parametrize("fuse", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,steps", [((16, 16, 16), 50), ((24, 20, 28), 7), ((64, 64, 64), 12),
+                                         ((9, 34, 130), 8), ((32, 16, 256), 6), ((5, 40, 260), 9),
+                                         ((40, 100, 128), 5)])
+def test_fused_sweeps_are_bitwise_equal_to_single_steps(gpu_fb, fuse, shape, steps):
+    """Temporal blocking (T steps per sweep) must not change a single bit: halo rows/columns,
+    periodic wrap in all three axes, ragged tiles, remainders (steps % T != 0)."""
+    rng = np.random.default_rng(SEED + 20)
+    a = rng.random(shape)
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, shape) as up:
+        up.set_fuse(fuse)
+        up.set_field(a)
+        up.advect(steps, up.default_dt())
+        f = up.field()
+    assert np.array_equal(f, C.upwind_advect(a, steps))
+
+
+def test_fused_config1_golden(gpu_fb):
+    g = golden("upwind_128_s100.npz")
+    for fuse in (2, 3, 4):
+        with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [128] * 3) as up:
+            up.set_fuse(fuse)
+            up.advect(100, up.default_dt())
+            f = up.field()
+            assert np.array_equal(f[:101, :101, :101], g["corner"])
+            assert np.count_nonzero(f) == int(g["nnz"])
+            assert up.checksum() == pytest.approx(float(g["checksum"]), rel=RTOL)
+
+
+def test_fuse_argument_validation(gpu_fb):
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [16, 16, 16]) as up:
+        with pytest.raises(gpu_fb.FdbError):
+            up.set_fuse(-1)
+        with pytest.raises(gpu_fb.FdbError):
+            up.set_fuse(9)
+        up.set_fuse(0)  # auto
+    with gpu_fb.Upwind([1.0, -1.0, 1.0], [1.0] * 3, [16, 16, 16]) as up:
+        with pytest.raises(gpu_fb.FdbError):
+            up.set_fuse(2)  # negative velocity: no TMA path, no fused path
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+@pytest.mark.parametrize("fuse", [2, 3])
+def test_fused_in_process_slabs(gpu_fb, ngpus, fuse):
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(SEED + 21)
+    a = rng.random((8 * ngpus, 24, 64))
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, ngpus=ngpus) as up:
+        up.set_fuse(fuse)
+        up.set_field(a)
+        up.advect(8 * ngpus + 5, up.default_dt())
+        f = up.field()
+    assert np.array_equal(f, C.upwind_advect(a, 8 * ngpus + 5))
