@@ -149,7 +149,9 @@ int stencil_common_create(int ndims, const int64_t* dims, int nbranch, const int
   if (nbranch < 1 || nbranch > 32)
     return set_error(FDB_E_INVALID, "nbranch must be in 1..32 (got %d)", nbranch);
   Geometry geo;
-  FDB_TRY(make_geometry(ndims, dims, &geo));
+  // a 2-D problem on one device is carried as a single plane so that the tiled kernel runs
+  // (the reference's default laplacian case is 2-D, ref: laplacian.cxx:41-42)
+  FDB_TRY(make_geometry(ndims, dims, &geo, /*plane2d=*/ndims == 2 && !comm && ngpus == 1));
   fdb_stencil* h = new (std::nothrow) fdb_stencil();
   if (!h) return set_error(FDB_E_OOM, "out of host memory");
   h->ndims = ndims;

@@ -50,7 +50,8 @@ int64_t launch_count();
 
 // ---- geometry of one engine -------------------------------------------------
 // Every problem is carried as a 3-D row-major box (n0, n1, n2), n2 fastest.
-// ndims == 2 maps (d0, d1) -> (d0, 1, d1) and ndims == 1 maps (d0) -> (1, 1, d0),
+// ndims == 2 maps (d0, d1) -> (d0, 1, d1) (or (1, d0, d1) on a single device, see plane2d)
+// and ndims == 1 maps (d0) -> (1, 1, d0),
 // so the reference's last axis is always the contiguous one and its first axis
 // (when it exists beside another) is the slab axis.  `axis_of[j]` is the
 // internal axis of reference axis j.
@@ -62,7 +63,8 @@ struct Geometry {
   int64_t plane() const { return n[1] * n[2]; }
   int64_t total() const { return n[0] * n[1] * n[2]; }
 };
-int make_geometry(int ndims, const int64_t* dims, Geometry* g);
+// plane2d: carry a 2-D problem as ONE plane (1, d0, d1) instead of d0 planes of one row
+int make_geometry(int ndims, const int64_t* dims, Geometry* g, bool plane2d = false);
 
 // ---- communicator (one process per GPU) -------------------------------------
 }  // namespace fdb
@@ -92,6 +94,13 @@ struct Slab {
   cudaEvent_t ev_bnd_done = nullptr;                // boundary planes of the next field written
   cudaEvent_t ev_ghost_ready[2] = {nullptr, nullptr};  // ghosts of buf[p] filled
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;     // timing
+  // direct halo transport: 64-bit sequence counters in THIS slab's memory, written by the
+  // neighbours (stream memory operations), and the neighbours' buffers/counters mapped here
+  // (plain peer pointers in one process, CUDA IPC mappings between processes)
+  uint64_t* flags = nullptr;
+  double* nbr_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [0 = prev, 1 = next][parity]
+  uint64_t* nbr_flags[2] = {nullptr, nullptr};
+  void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // TMA descriptors, index = buffer parity
   // (several box shapes over the same tensors, see kernels_tma.cu)
   CUtensorMap tm_body[2];  // local planes, box = tile rows
@@ -119,6 +128,9 @@ struct Field {
   int nparts = 1;           // total slabs in the ring
   std::vector<Slab> slabs;
   int cur = 0;              // buf[cur] holds the current field
+  bool direct = true;       // halo transport: peer copies + stream flags (else NCCL / event-ordered copies)
+  uint64_t xseq = 0;        // halo exchanges issued so far (same on every rank)
+  uint64_t ghost_seq[2] = {0, 0};  // the exchange that filled the ghosts of buf[p]
   bool ghosts_valid = false;
   double last_ms = 0, last_updates = 0, last_halo_bytes = 0;
 

@@ -34,9 +34,10 @@ using namespace ptx;
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int T_, int CJ_, int R_, int STAGES_>
+template <int T_, int CJ_, int R_, int STAGES_, bool SHFL_ = false>
 struct FusedCfg {
   static constexpr int T = T_, CJ = CJ_, R = R_, STAGES = STAGES_;
+  static constexpr bool SHFL = SHFL_;                  // k-1 neighbour by warp shuffle instead of LDS.64
   static constexpr int BK = 128;                       // output cells per tile row
   static constexpr int HKC = 2 * (T / 2);              // redundant compute columns (even, >= T-1)
   static constexpr int HKI = HKC + 2;                  // input halo columns (even, >= T)
@@ -206,7 +207,14 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         for (int r = 0; r < C::R; ++r) {
           const int s = q0 + r + 1;
           v[r] = lds_v2((own_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 2) * 8);
-          km[r] = lds_f64((km_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 1) * 8);
+          if (C::SHFL) {
+            // the cell to the left is the previous lane's second cell; only a warp's first
+            // lane (and a row's first thread) reads it from shared memory
+            km[r] = __shfl_up_sync(0xffffffffu, v[r].y, 1);
+            if (lane == 0 || tx == 0) km[r] = lds_f64((km_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 1) * 8);
+          } else {
+            km[r] = lds_f64((km_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 1) * 8);
+          }
         }
       }
       __syncwarp();
@@ -240,11 +248,15 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 #pragma unroll
             for (int r = 0; r < C::R; ++r) sts_v2(xb + x_own + r * C::XP, nv[r].x, nv[r].y);
           }
+          if (C::SHFL) {
+#pragma unroll
+            for (int r = 0; r < C::R; ++r) km[r] = __shfl_up_sync(0xffffffffu, nv[r].y, 1);
+          }
           named_bar_sync(1, C::CONSUMERS);
           up = lds_v2(xb + x_up);
 #pragma unroll
           for (int r = 0; r < C::R; ++r) {
-            km[r] = lds_f64(xb + x_km + r * C::XP);
+            if (!C::SHFL || lane == 0) km[r] = lds_f64(xb + x_km + r * C::XP);
             v[r] = nv[r];
           }
         }
@@ -275,6 +287,8 @@ const FusedConfig kFused2[] = {
     make_fused<FusedCfg<2, 16, 2, 6>>("t2_cj16_r2_s6"),
     make_fused<FusedCfg<2, 24, 3, 4>>("t2_cj24_r3_s4"),
     make_fused<FusedCfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),
+    make_fused<FusedCfg<2, 16, 2, 4, true>>("t2_cj16_r2_s4_shfl"),
+    make_fused<FusedCfg<2, 21, 3, 5, true>>("t2_cj21_r3_s5_shfl"),
 };
 const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // round-1 best: 900 GCUPS at 512^3 / 1024^3
@@ -286,6 +300,8 @@ const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 21, 3, 5>>("t3_cj21_r3_s5"),
     make_fused<FusedCfg<3, 24, 3, 4>>("t3_cj24_r3_s4"),
     make_fused<FusedCfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
+    make_fused<FusedCfg<3, 21, 3, 4, true>>("t3_cj21_r3_s4_shfl"),
+    make_fused<FusedCfg<3, 16, 2, 4, true>>("t3_cj16_r2_s4_shfl"),
 };
 const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
@@ -294,6 +310,8 @@ const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 28, 4, 3>>("t4_cj28_r4_s3"),
     make_fused<FusedCfg<4, 16, 4, 4>>("t4_cj16_r4_s4"),
     make_fused<FusedCfg<4, 21, 3, 3>>("t4_cj21_r3_s3"),
+    make_fused<FusedCfg<4, 21, 3, 4, true>>("t4_cj21_r3_s4_shfl"),
+    make_fused<FusedCfg<4, 16, 2, 4, true>>("t4_cj16_r2_s4_shfl"),
 };
 
 const FusedConfig* fused_table(int T, int* count) {
@@ -392,7 +410,12 @@ int launch_upwind_fused(Field& f, int d, int T, int64_t ibeg, int64_t iend, cons
   a.c0 = k.c[0];
   a.c1 = k.c[1];
   a.c2 = k.c[2];
-  const int64_t grid_max = (int64_t)at.ctas_per_sm * at.sms;
+  // The direct halo transport runs on copy engines and needs no SM.  With the NCCL transport
+  // the send/recv kernels must find free SMs while the persistent interior kernel runs:
+  // FDB_COMM_SMS leaves some unoccupied (mind the extra round a smaller grid can cost).
+  const int reserve = f.single() ? 0 : env_int2("FDB_COMM_SMS", 0);
+  int64_t grid_max = (int64_t)at.ctas_per_sm * (at.sms - reserve);
+  if (grid_max < 1) grid_max = 1;
   const int64_t tiles = (int64_t)a.njt * a.nkt;
   const int64_t planes = iend - ibeg;
   int64_t ci = env_int2("FDB_TMA_CI", 0);

@@ -245,6 +245,7 @@ struct Lap7Args {
   int G;
   double w[7];
   int has[7];  // branch present in the stencil map (absent branches are skipped, not added as 0)
+  int skip_lo, skip_hi;  // no (-1,0,0) / (1,0,0) branch: the planes outside a chunk are not even loaded
 };
 
 // acc = 0; for each present branch in order: acc = acc + w * in[...]   (ref: Filter.cpp:247-251)
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(C::THREADS)
         const int jm = (j0 == 0) ? (int)a.n1 - 1 : j0 - 1;
         const int jp = (j0 + C::BJ >= (int)a.n1) ? 0 : j0 + C::BJ;
         const bool first_k = (kt == 0), last_k = (kt == a.nkt - 1);
-        for (int64_t i = i0 - 1; i <= i1; ++i) {
+        for (int64_t i = (a.skip_lo ? i0 : i0 - 1); i <= (a.skip_hi ? i1 - 1 : i1); ++i) {
           mbar_wait(empty + 8 * stage, phase ^ 1);
           const uint32_t st = smem + stage * C::STAGE_BYTES;
           const uint32_t fb = full + 8 * stage;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(C::THREADS)
 
     double2 below[C::R];    // plane i-1
     double2 partial[C::R];  // first six branches of plane i-1's output (waiting for plane i)
-    {
+    if (!a.skip_lo) {
       mbar_wait(full + 8 * stage, phase);
       const uint32_t st = smem + stage * C::STAGE_BYTES;
 #pragma unroll
@@ -350,78 +351,76 @@ __global__ void __launch_bounds__(C::THREADS)
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + 8 * stage);
       if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) below[r] = make_double2(0.0, 0.0);
     }
 
-    for (int64_t i = i0; i <= i1; ++i) {
-      mbar_wait(full + 8 * stage, phase);
-      const uint32_t st = smem + stage * C::STAGE_BYTES;
-      double2 ctr[C::R];
-      if (i == i1) {
-        // plane above the chunk: finishes the last output plane
-#pragma unroll
-        for (int r = 0; r < C::R; ++r) ctr[r] = lds_v2(st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES + col);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + 8 * stage);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-      } else {
-        double km1[C::R], kp1[C::R];
-        const uint32_t up_row = (r0 == 0) ? st + C::TOP_OFF : st + C::BODY_OFF + (r0 - 1) * C::ROW_BYTES;
-        const uint32_t dn_row =
-            (r0 + C::R == C::BJ) ? st + C::BOT_OFF : st + C::BODY_OFF + (r0 + C::R) * C::ROW_BYTES;
-        const double2 up = lds_v2(up_row + col);
-        const double2 dn = lds_v2(dn_row + col);
-#pragma unroll
-        for (int r = 0; r < C::R; ++r) {
-          const uint32_t row = st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES;
-          ctr[r] = lds_v2(row + col);
-          km1[r] = lds_f64(wrapl_lane ? st + C::WRAPL_OFF + (r0 + r) * 16 + 8 : row + col - 8);
-          kp1[r] = lds_f64(wrapr_lane ? st + C::WRAPR_OFF + (r0 + r) * 16 : row + col + 16);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + 8 * stage);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-
-        // finish and store plane i-1 (needs this plane's centre), then start plane i
-        if (i > i0) {
-          double* orow = a.out + ((i - 1) * a.n1 + j) * a.n2 + k;
-#pragma unroll
-          for (int r = 0; r < C::R; ++r) {
-            double x = partial[r].x, y = partial[r].y;
-            if (a.has[6]) {
-              x = __dadd_rn(x, __dmul_rn(a.w[6], ctr[r].x));
-              y = __dadd_rn(y, __dmul_rn(a.w[6], ctr[r].y));
-            }
-            st_global_v2(orow + (int64_t)r * a.n2, x, y);
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < C::R; ++r) {
-          const double2 jm = (r == 0) ? up : ctr[r - 1];
-          const double2 jp = (r == C::R - 1) ? dn : ctr[r + 1];
-          double x = 0.0, y = 0.0;
-          if (a.has[0]) { x = __dadd_rn(x, __dmul_rn(a.w[0], below[r].x)); y = __dadd_rn(y, __dmul_rn(a.w[0], below[r].y)); }
-          if (a.has[1]) { x = __dadd_rn(x, __dmul_rn(a.w[1], jm.x));       y = __dadd_rn(y, __dmul_rn(a.w[1], jm.y)); }
-          if (a.has[2]) { x = __dadd_rn(x, __dmul_rn(a.w[2], km1[r]));     y = __dadd_rn(y, __dmul_rn(a.w[2], ctr[r].x)); }
-          if (a.has[3]) { x = __dadd_rn(x, __dmul_rn(a.w[3], ctr[r].x));   y = __dadd_rn(y, __dmul_rn(a.w[3], ctr[r].y)); }
-          if (a.has[4]) { x = __dadd_rn(x, __dmul_rn(a.w[4], ctr[r].y));   y = __dadd_rn(y, __dmul_rn(a.w[4], kp1[r])); }
-          if (a.has[5]) { x = __dadd_rn(x, __dmul_rn(a.w[5], jp.x));       y = __dadd_rn(y, __dmul_rn(a.w[5], jp.y)); }
-          partial[r].x = x;
-          partial[r].y = y;
-          below[r] = ctr[r];
-        }
-        continue;
-      }
-      // i == i1: finish plane i1-1
-      double* orow = a.out + ((i - 1) * a.n1 + j) * a.n2 + k;
+    // finish plane `ip` with the (i+1) branch taken from `above`, and store it
+    auto finish = [&](int64_t ip, const double2* above) {
+      double* orow = a.out + (ip * a.n1 + j) * a.n2 + k;
 #pragma unroll
       for (int r = 0; r < C::R; ++r) {
         double x = partial[r].x, y = partial[r].y;
         if (a.has[6]) {
-          x = __dadd_rn(x, __dmul_rn(a.w[6], ctr[r].x));
-          y = __dadd_rn(y, __dmul_rn(a.w[6], ctr[r].y));
+          x = __dadd_rn(x, __dmul_rn(a.w[6], above[r].x));
+          y = __dadd_rn(y, __dmul_rn(a.w[6], above[r].y));
         }
         st_global_v2(orow + (int64_t)r * a.n2, x, y);
       }
+    };
+
+    for (int64_t i = i0; i < i1; ++i) {
+      mbar_wait(full + 8 * stage, phase);
+      const uint32_t st = smem + stage * C::STAGE_BYTES;
+      double2 ctr[C::R];
+      double km1[C::R], kp1[C::R];
+      const uint32_t up_row = (r0 == 0) ? st + C::TOP_OFF : st + C::BODY_OFF + (r0 - 1) * C::ROW_BYTES;
+      const uint32_t dn_row =
+          (r0 + C::R == C::BJ) ? st + C::BOT_OFF : st + C::BODY_OFF + (r0 + C::R) * C::ROW_BYTES;
+      const double2 up = lds_v2(up_row + col);
+      const double2 dn = lds_v2(dn_row + col);
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        const uint32_t row = st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES;
+        ctr[r] = lds_v2(row + col);
+        km1[r] = lds_f64(wrapl_lane ? st + C::WRAPL_OFF + (r0 + r) * 16 + 8 : row + col - 8);
+        kp1[r] = lds_f64(wrapr_lane ? st + C::WRAPR_OFF + (r0 + r) * 16 : row + col + 16);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+
+      // plane i-1 was waiting for this plane's centre
+      if (!a.skip_hi && i > i0) finish(i - 1, ctr);
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        const double2 jm = (r == 0) ? up : ctr[r - 1];
+        const double2 jp = (r == C::R - 1) ? dn : ctr[r + 1];
+        double x = 0.0, y = 0.0;
+        if (a.has[0]) { x = __dadd_rn(x, __dmul_rn(a.w[0], below[r].x)); y = __dadd_rn(y, __dmul_rn(a.w[0], below[r].y)); }
+        if (a.has[1]) { x = __dadd_rn(x, __dmul_rn(a.w[1], jm.x));       y = __dadd_rn(y, __dmul_rn(a.w[1], jm.y)); }
+        if (a.has[2]) { x = __dadd_rn(x, __dmul_rn(a.w[2], km1[r]));     y = __dadd_rn(y, __dmul_rn(a.w[2], ctr[r].x)); }
+        if (a.has[3]) { x = __dadd_rn(x, __dmul_rn(a.w[3], ctr[r].x));   y = __dadd_rn(y, __dmul_rn(a.w[3], ctr[r].y)); }
+        if (a.has[4]) { x = __dadd_rn(x, __dmul_rn(a.w[4], ctr[r].y));   y = __dadd_rn(y, __dmul_rn(a.w[4], kp1[r])); }
+        if (a.has[5]) { x = __dadd_rn(x, __dmul_rn(a.w[5], jp.x));       y = __dadd_rn(y, __dmul_rn(a.w[5], jp.y)); }
+        partial[r].x = x;
+        partial[r].y = y;
+        below[r] = ctr[r];
+      }
+      if (a.skip_hi) finish(i, ctr);  // no (i+1) branch: the sum is complete
+    }
+    if (!a.skip_hi) {
+      // plane above the chunk: finishes the last output plane
+      mbar_wait(full + 8 * stage, phase);
+      const uint32_t st = smem + stage * C::STAGE_BYTES;
+      double2 ctr[C::R];
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) ctr[r] = lds_v2(st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES + col);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      finish(i1 - 1, ctr);
     }
   }
 }
@@ -536,7 +535,9 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
   a.c2 = k.c[2];
   // i-chunk: long enough to amortise the extra plane each work item reads,
   // short enough that every CTA gets several items (static round-robin).
-  const int64_t grid_max = (int64_t)at.ctas_per_sm * at.sms;
+  const int reserve = f.single() ? 0 : env_int("FDB_COMM_SMS", 0);  // SMs left free for NCCL halo kernels (see kernels_fused.cu)
+  int64_t grid_max = (int64_t)at.ctas_per_sm * (at.sms - reserve);
+  if (grid_max < 1) grid_max = 1;
   const int64_t tiles = (int64_t)a.njt * a.nkt;
   const int64_t planes = iend - ibeg;
   int64_t ci = env_int("FDB_TMA_CI", 0);
@@ -604,7 +605,8 @@ int lap7_pick_cfg(const Field& f) {
 int tma_encode_slab_lap7(Field* f, int d) {
   Slab& s = f->slabs[d];
   s.have_tma = false;
-  if (f->geo.ndims != 3 || f->G != 1) return FDB_OK;
+  const bool plane2d = f->geo.ndims == 2 && f->geo.n[0] == 1;
+  if ((f->geo.ndims != 3 && !plane2d) || f->G != 1) return FDB_OK;
   const int c = lap7_pick_cfg(*f);
   if (c < 0) return FDB_OK;
   s.tma_cfg = c;
@@ -623,7 +625,8 @@ int tma_encode_slab_lap7(Field* f, int d) {
 }
 
 bool stencil_lap7_supported(const Field& f, const StencilBranches& b) {
-  if (f.geo.ndims != 3 || f.G != 1) return false;
+  const bool plane2d = f.geo.ndims == 2 && f.geo.n[0] == 1;
+  if ((f.geo.ndims != 3 && !plane2d) || f.G != 1) return false;
   if (f.slabs.empty() || !f.slabs[0].have_tma) return false;
   if (b.nbranch < 1 || b.nbranch > 7) return false;
   int seen = 0;
@@ -667,7 +670,11 @@ int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const
     a.w[slot] = b.w[i];
     a.has[slot] = 1;
   }
-  const int64_t grid_max = (int64_t)at.ctas_per_sm * at.sms;
+  a.skip_lo = !a.has[0];
+  a.skip_hi = !a.has[6];
+  const int reserve = f.single() ? 0 : env_int("FDB_COMM_SMS", 0);  // SMs left free for NCCL halo kernels (see kernels_fused.cu)
+  int64_t grid_max = (int64_t)at.ctas_per_sm * (at.sms - reserve);
+  if (grid_max < 1) grid_max = 1;
   const int64_t tiles = (int64_t)a.njt * a.nkt;
   const int64_t planes = iend - ibeg;
   int64_t ci = env_int("FDB_TMA_CI", 0);

@@ -31,7 +31,7 @@ void count_launch(int64_t n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAX
 int64_t launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 // ---- geometry ---------------------------------------------------------------------
-int make_geometry(int ndims, const int64_t* dims, Geometry* g) {
+int make_geometry(int ndims, const int64_t* dims, Geometry* g, bool plane2d) {
   if (ndims < 1 || ndims > 3) return set_error(FDB_E_INVALID, "ndims must be 1, 2 or 3 (got %d)", ndims);
   if (!dims) return set_error(FDB_E_INVALID, "null dimensions");
   for (int j = 0; j < ndims; ++j)
@@ -40,6 +40,11 @@ int make_geometry(int ndims, const int64_t* dims, Geometry* g) {
   g->ndims = ndims;
   if (ndims == 3) {
     for (int j = 0; j < 3; ++j) { g->n[j] = dims[j]; g->axis_of[j] = j; }
+  } else if (ndims == 2 && plane2d) {
+    // one plane: both axes are in-plane, so the tiled (TMA) kernels apply; no slab axis
+    g->n[0] = 1; g->n[1] = dims[0]; g->n[2] = dims[1];
+    g->axis_of[0] = 1; g->axis_of[1] = 2;
+    g->active[0] = false;
   } else if (ndims == 2) {
     g->n[0] = dims[0]; g->n[1] = 1; g->n[2] = dims[1];
     g->axis_of[0] = 0; g->axis_of[1] = 2;
@@ -86,6 +91,93 @@ int encode_tensor_map_3d(CUtensorMap* tm, const double* base, int64_t n2, int64_
   if (r != CUDA_SUCCESS)
     return set_error(FDB_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lldx%lld box=%dx%d",
                      (int)r, (long long)n0, (long long)n1, (long long)n2, box1, box2);
+  return FDB_OK;
+}
+
+// ---- stream memory operations (driver API, resolved at run time) -------------------------
+enum { F_GHOST_LO = 0, F_GHOST_HI = 1, F_ACK_NEXT = 2, F_ACK_PREV = 3, F_COUNT = 8 };
+enum { NBR_PREV = 0, NBR_NEXT = 1 };
+
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+static StreamValueFn g_wait_value = nullptr, g_write_value = nullptr;
+
+static bool stream_memops_available() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_wait_value = reinterpret_cast<StreamValueFn>(p);
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_write_value = reinterpret_cast<StreamValueFn>(p);
+    (void)cudaGetLastError();
+  });
+  return g_wait_value && g_write_value;
+}
+
+// stream `s` proceeds once *addr >= v
+static int stream_wait_geq(cudaStream_t s, uint64_t* addr, uint64_t v) {
+  CUresult r = g_wait_value((CUstream)s, (CUdeviceptr)(uintptr_t)addr, v, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) return set_error(FDB_E_CUDA, "cuStreamWaitValue64 failed (CUresult %d)", (int)r);
+  return FDB_OK;
+}
+// *addr = v once everything before it in `s` is done and visible
+static int stream_write(cudaStream_t s, uint64_t* addr, uint64_t v) {
+  CUresult r = g_write_value((CUstream)s, (CUdeviceptr)(uintptr_t)addr, v, CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS) return set_error(FDB_E_CUDA, "cuStreamWriteValue64 failed (CUresult %d)", (int)r);
+  return FDB_OK;
+}
+
+// Map the neighbours' buffers and counters of a one-slab-per-process field into this
+// process (CUDA IPC); the handles travel through one NCCL all-gather.
+static int field_open_neighbours_ipc(Field* f) {
+  Slab& s = f->slabs[0];
+  fdb_comm* c = f->comm;
+  const int n = c->nranks;
+  struct Pack { cudaIpcMemHandle_t h[3]; };
+  static_assert(sizeof(Pack) % sizeof(double) == 0, "pack size");
+  const size_t words = sizeof(Pack) / sizeof(double);
+  Pack mine;
+  FDB_CUDA(cudaIpcGetMemHandle(&mine.h[0], s.buf[0]));
+  FDB_CUDA(cudaIpcGetMemHandle(&mine.h[1], s.buf[1]));
+  FDB_CUDA(cudaIpcGetMemHandle(&mine.h[2], s.flags));
+  double *dsend = nullptr, *drecv = nullptr;
+  FDB_CUDA(cudaMalloc(&dsend, sizeof(Pack)));
+  FDB_CUDA(cudaMalloc(&drecv, sizeof(Pack) * (size_t)n));
+  FDB_CUDA(cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice));
+  FDB_NCCL(ncclAllGather(dsend, drecv, words, ncclDouble, c->nccl, c->stream));
+  FDB_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<Pack> all((size_t)n);
+  FDB_CUDA(cudaMemcpy(all.data(), drecv, sizeof(Pack) * (size_t)n, cudaMemcpyDeviceToHost));
+  cudaFree(dsend);
+  cudaFree(drecv);
+  const int prev = (c->rank + n - 1) % n, next = (c->rank + 1) % n;
+  int opened = 0;
+  auto open3 = [&](int rank, int side) -> int {
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; ++k) {
+      cudaError_t e = cudaIpcOpenMemHandle(&p[k], all[(size_t)rank].h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return set_error(FDB_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", rank, cudaGetErrorString(e));
+      }
+      s.ipc_opened[opened++] = p[k];
+    }
+    s.nbr_buf[side][0] = static_cast<double*>(p[0]);
+    s.nbr_buf[side][1] = static_cast<double*>(p[1]);
+    s.nbr_flags[side] = static_cast<uint64_t*>(p[2]);
+    return FDB_OK;
+  };
+  FDB_TRY(open3(next, NBR_NEXT));
+  if (prev == next) {  // two ranks: one neighbour on both sides, one mapping
+    s.nbr_buf[NBR_PREV][0] = s.nbr_buf[NBR_NEXT][0];
+    s.nbr_buf[NBR_PREV][1] = s.nbr_buf[NBR_NEXT][1];
+    s.nbr_flags[NBR_PREV] = s.nbr_flags[NBR_NEXT];
+  } else {
+    FDB_TRY(open3(prev, NBR_PREV));
+  }
   return FDB_OK;
 }
 
@@ -150,6 +242,8 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
     const int64_t nchunk = reduce_partials_per_plane(plane);
     FDB_CUDA(cudaMalloc(&s.partial, (size_t)(nloc * nchunk) * sizeof(double)));
     FDB_CUDA(cudaMalloc(&s.plane_sums, (size_t)nloc * sizeof(double)));
+    FDB_CUDA(cudaMalloc(&s.flags, F_COUNT * sizeof(uint64_t)));
+    FDB_CUDA(cudaMemset(s.flags, 0, F_COUNT * sizeof(uint64_t)));
     int lo_prio = 0, hi_prio = 0;
     FDB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
     FDB_CUDA(cudaStreamCreateWithPriority(&s.s_main, cudaStreamNonBlocking, lo_prio));
@@ -184,6 +278,33 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
       }
     }
   }
+  // halo transport
+  const char* halo_env = getenv("FDB_HALO");
+  f->direct = !(halo_env && strcmp(halo_env, "nccl") == 0) && stream_memops_available();
+  if (f->nparts > 1 && f->direct) {
+    if (comm) {
+      int rc = field_open_neighbours_ipc(f);
+      int ok = (rc == FDB_OK) ? 1 : 0, all_ok = ok;
+      {  // every rank must take the same transport
+        int* dflag = reinterpret_cast<int*>(comm->scratch);
+        FDB_CUDA(cudaMemcpy(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice));
+        FDB_NCCL(ncclAllReduce(dflag, dflag + 1, 1, ncclInt, ncclMin, comm->nccl, comm->stream));
+        FDB_CUDA(cudaStreamSynchronize(comm->stream));
+        FDB_CUDA(cudaMemcpy(&all_ok, dflag + 1, sizeof(int), cudaMemcpyDeviceToHost));
+      }
+      if (!all_ok) f->direct = false;  // e.g. no IPC between these processes: NCCL send/recv instead
+    } else {
+      const int g = f->ngpus;
+      for (int d = 0; d < g; ++d) {
+        Slab& s = f->slabs[d];
+        const Slab& pv = f->slabs[(d + g - 1) % g];
+        const Slab& nx = f->slabs[(d + 1) % g];
+        for (int p = 0; p < 2; ++p) { s.nbr_buf[NBR_PREV][p] = pv.buf[p]; s.nbr_buf[NBR_NEXT][p] = nx.buf[p]; }
+        s.nbr_flags[NBR_PREV] = pv.flags;
+        s.nbr_flags[NBR_NEXT] = nx.flags;
+      }
+    }
+  }
   for (int d = 0; d < f->ngpus; ++d) {
     if (want_tma == 1) FDB_TRY(tma_encode_slab(f, d));
     if (want_tma == 2) FDB_TRY(tma_encode_slab_lap7(f, d));
@@ -195,6 +316,17 @@ void field_destroy(Field* f) {
   for (auto& s : f->slabs) {
     cudaSetDevice(s.device);
     cudaDeviceSynchronize();
+  }
+  if (f->comm && f->comm->nranks > 1 && f->direct && !f->slabs.empty()) {
+    // neighbours write into this slab's memory: nobody frees before everybody is done
+    double v = 0.0;
+    fdb_comm_max(f->comm, &v);
+  }
+  for (auto& s : f->slabs) {
+    cudaSetDevice(s.device);
+    for (void*& p : s.ipc_opened)
+      if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    if (s.flags) cudaFree(s.flags);
     for (int p = 0; p < 2; ++p) if (s.buf[p]) cudaFree(s.buf[p]);
     if (s.partial) cudaFree(s.partial);
     if (s.plane_sums) cudaFree(s.plane_sums);
@@ -238,6 +370,19 @@ int field_sync(Field* f) {
   return FDB_OK;
 }
 
+// direct transport: tell the producers of this slab's ghosts that the round of exchange
+// `xseq` is complete here (everything enqueued on s_main so far), so they may overwrite the
+// ghost planes that round was reading
+static int field_ack(Field* f) {
+  if (f->single() || !f->direct) return FDB_OK;
+  for (auto& s : f->slabs) {
+    FDB_CUDA(cudaSetDevice(s.device));
+    if (f->need_lo) FDB_TRY(stream_write(s.s_main, &s.nbr_flags[NBR_PREV][F_ACK_NEXT], f->xseq));
+    if (f->need_hi) FDB_TRY(stream_write(s.s_main, &s.nbr_flags[NBR_NEXT][F_ACK_PREV], f->xseq));
+  }
+  return FDB_OK;
+}
+
 // After a host-driven overwrite of buf[p] (upload, reset): publish it.
 static int field_publish(Field* f, int p) {
   for (auto& s : f->slabs) {
@@ -245,7 +390,8 @@ static int field_publish(Field* f, int p) {
     FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
   }
   f->cur = p;
-  return field_exchange(f, p, /*after_bnd=*/false, f->G);
+  FDB_TRY(field_exchange(f, p, /*after_bnd=*/false, f->G));
+  return field_ack(f);
 }
 
 int field_upload(Field* f, int p, const double* host_global, const double* host_slab) {
@@ -300,6 +446,34 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
   const size_t bytes = (size_t)depth * (size_t)plane * sizeof(double);
   const int64_t gcount = (int64_t)depth * plane;
   const int64_t lo_skip = (int64_t)(f->G - depth) * plane;  // the ghost planes nearest the body
+  if (f->direct) {
+    // Push model on copy engines: each slab copies its boundary planes straight into the
+    // neighbour's ghost planes (no SM is needed, so the transfer overlaps a persistent interior
+    // kernel that owns every SM) and bumps the neighbour's sequence counter behind the copy.
+    const uint64_t e = ++f->xseq;
+    for (int d = 0; d < f->ngpus; ++d) {
+      Slab& s = f->slabs[d];
+      FDB_CUDA(cudaSetDevice(s.device));
+      if (!after_bnd) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
+      const int64_t nloc = s.nloc();
+      if (f->need_lo) {
+        // WAR on the neighbour's ghost planes: it has finished the round before this one
+        FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_ACK_NEXT], e - 1));
+        FDB_CUDA(cudaMemcpyAsync(s.nbr_buf[NBR_NEXT][p] + lo_skip, f->body(d, p) + (nloc - depth) * plane, bytes,
+                                 cudaMemcpyDeviceToDevice, s.s_bnd));
+        FDB_TRY(stream_write(s.s_bnd, &s.nbr_flags[NBR_NEXT][F_GHOST_LO], e));
+      }
+      if (f->need_hi) {
+        FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_ACK_PREV], e - 1));
+        FDB_CUDA(cudaMemcpyAsync(s.nbr_buf[NBR_PREV][p] + (int64_t)(f->G + nloc) * plane, f->body(d, p), bytes,
+                                 cudaMemcpyDeviceToDevice, s.s_bnd));
+        FDB_TRY(stream_write(s.s_bnd, &s.nbr_flags[NBR_PREV][F_GHOST_HI], e));
+      }
+      f->last_halo_bytes += (double)bytes * ((f->need_lo ? 1 : 0) + (f->need_hi ? 1 : 0));
+    }
+    f->ghost_seq[p] = e;
+    return FDB_OK;
+  }
   if (f->comm) {
     Slab& s = f->slabs[0];
     fdb_comm* c = f->comm;
@@ -369,8 +543,13 @@ int field_sweep(Field* f, SweepLauncher* L, int depth) {
     const int64_t b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
     const int64_t t_beg = f->need_lo ? (nloc - depth > b_end ? nloc - depth : b_end) : nloc;
     FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
-    FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_ghost_ready[X], 0));
-    if (!f->comm) {
+    if (f->direct) {
+      if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_LO], f->ghost_seq[X]));
+      if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_HI], f->ghost_seq[X]));
+    } else {
+      FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_ghost_ready[X], 0));
+    }
+    if (!f->comm && !f->direct) {
       // WAR on the planes about to be rewritten: the neighbours' last pull of
       // them (two sweeps ago, same buffer) must have finished.  NCCL sends are
       // ordered by s_bnd itself.
@@ -391,12 +570,17 @@ int field_sweep(Field* f, SweepLauncher* L, int depth) {
     const int64_t nloc = s.nloc();
     const int64_t b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
     const int64_t t_beg = f->need_lo ? (nloc - depth > b_end ? nloc - depth : b_end) : nloc;
-    FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_ghost_ready[X], 0));
+    if (f->direct) {
+      if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_main, &s.flags[F_GHOST_LO], f->ghost_seq[X]));
+      if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_main, &s.flags[F_GHOST_HI], f->ghost_seq[X]));
+    } else {
+      FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_ghost_ready[X], 0));
+    }
     FDB_TRY(L->launch(f, d, b_end, t_beg, s.s_main));
     FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_bnd_done, 0));
     FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
   }
-  return FDB_OK;
+  return field_ack(f);
 }
 
 // ---- reductions -------------------------------------------------------------------------

@@ -183,3 +183,23 @@ def test_laplacian_128_ten_applies_noise_dominated_still_bitwise(gpu_fb):
         r = C.stencil_apply(r, off, w)
     assert np.array_equal(y10, r)
     assert np.abs(y10).max() == 1.2084444224735869e-06
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (48, 64), (16, 32), (80, 192)])
+def test_two_d_laplacian_takes_the_tiled_kernel(gpu_fb, shape):
+    """The reference's default laplacian case is 2-D (laplacian.cxx:41-42); on one device it is
+    carried as a single plane and runs the TMA kernel with the i-branches masked out."""
+    rng = np.random.default_rng(SEED + 12)
+    a = rng.random(shape)
+    off, w = oracle.laplacian_stencil(2)
+    with gpu_fb.Filter(shape, [0.0] * 2, [1.0] * 2, as_dict(off, w)) as fl:
+        assert fl.kernel() == gpu_fb.FDB_KERNEL_TMA
+        fl.set_input(a)
+        fl.iterate(5)
+        out = fl.get()
+        cs = fl.computeCheckSum("output")
+    ref = a
+    for _ in range(5):
+        ref = C.stencil_apply(ref, off, w)
+    assert np.array_equal(out, ref)
+    assert abs(cs - C.checksum(ref)) <= 1e-12 * max(1.0, np.abs(ref).sum())
