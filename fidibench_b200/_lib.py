@@ -66,6 +66,7 @@ _SIGS = {
     "fdb_upwind_local_range": (i32, [vp, p_i64, p_i64]),
     "fdb_upwind_set_field": (i32, [vp, vp]),
     "fdb_upwind_set_slab": (i32, [vp, vp]),
+    "fdb_upwind_set_slab_async": (i32, [vp, vp]),
     "fdb_upwind_reset": (i32, [vp]),
     "fdb_upwind_advect": (i32, [vp, i64, dbl]),
     "fdb_upwind_advect_async": (i32, [vp, i64, dbl]),

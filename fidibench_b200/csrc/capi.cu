@@ -34,20 +34,20 @@ namespace {
 struct UpwindSweep : SweepLauncher {
   UpwindCoeffs k;
   bool tma = false;
-  int T = 1;  // time steps per sweep (> 1: the fused temporal-blocking kernel)
-  int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) override {
-    if (T > 1) return launch_upwind_fused(*f, d, T, ibeg, iend, k, s);
-    return tma ? launch_upwind_tma(*f, d, ibeg, iend, k, s)
-               : launch_upwind_generic(*f, d, ibeg, iend, k, s);
+  // depth = time steps this sweep advances (> 1: the fused temporal-blocking kernel)
+  int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    if (depth > 1) return launch_upwind_fused(*f, d, X, depth, ibeg, iend, k, s);
+    return tma ? launch_upwind_tma(*f, d, X, ibeg, iend, k, s)
+               : launch_upwind_generic(*f, d, X, ibeg, iend, k, s);
   }
 };
 
 struct StencilSweep : SweepLauncher {
   const StencilBranches* b = nullptr;
   bool fast = false;
-  int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) override {
-    return fast ? launch_stencil_lap7(*f, d, ibeg, iend, *b, s)
-                : launch_stencil_generic(*f, d, ibeg, iend, *b, s);
+  int launch(Field* f, int d, int X, int /*depth*/, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    return fast ? launch_stencil_lap7(*f, d, X, ibeg, iend, *b, s)
+                : launch_stencil_generic(*f, d, X, ibeg, iend, *b, s);
   }
 };
 
@@ -366,6 +366,13 @@ int fdb_upwind_set_slab(fdb_upwind* h, const double* host_slab) {
   FDB_GUARD_END
 }
 
+int fdb_upwind_set_slab_async(fdb_upwind* h, const double* host_slab) {
+  FDB_GUARD_BEGIN
+  if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
+  return field_upload(&h->field, h->field.cur, nullptr, host_slab, /*async=*/true);
+  FDB_GUARD_END
+}
+
 int fdb_upwind_reset(fdb_upwind* h) {
   FDB_GUARD_BEGIN
   if (!h) return set_error(FDB_E_INVALID, "null handle");
@@ -448,16 +455,17 @@ int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTim
   sw.tma = (kern == FDB_KERNEL_TMA);
   const int want = (h->fuse == 0) ? kAutoFuse : h->fuse;
   const int fuse = (sw.tma && want > 1 && upwind_fused_supported(*f, sw.k, want)) ? want : 1;
-  FDB_TRY(timing_begin(f));
+  // plan: sweeps of `fuse` time steps, then the remainder
+  std::vector<int> depths;
   for (int64_t done = 0; done < numTimeSteps;) {
     const int64_t left = numTimeSteps - done;
     int t = (int)(left < fuse ? left : fuse);
     if (t > 1 && !upwind_fused_supported(*f, sw.k, t)) t = 1;
-    sw.T = t;
-    FDB_TRY(field_sweep(f, &sw, t));
-    f->cur = 1 - f->cur;
+    depths.push_back(t);
     done += t;
   }
+  FDB_TRY(timing_begin(f));
+  FDB_TRY(field_run_sweeps(f, &sw, depths.data(), (int)depths.size()));
   FDB_TRY(timing_end(f));
   f->last_updates = (double)numTimeSteps * (double)f->geo.total();
   return FDB_OK;
@@ -647,7 +655,9 @@ static int stencil_apply_async(fdb_stencil* h) {
   int kern = FDB_KERNEL_GENERIC;
   FDB_TRY(fdb_stencil_get_kernel(h, &kern));
   sw.fast = (kern == FDB_KERNEL_TMA);
-  FDB_TRY(field_sweep(f, &sw, f->G));
+  const int depth = f->G;
+  FDB_TRY(field_run_sweeps(f, &sw, &depth, 1));
+  f->cur = 1 - f->cur;  // an apply leaves `cur` on the input; the swap flips it (copyOutToIn)
   h->out_valid = true;
   return FDB_OK;
 }

@@ -92,6 +92,7 @@ struct Slab {
   bool own_main = true;
   cudaEvent_t ev_local_done = nullptr;              // all of the current field written
   cudaEvent_t ev_bnd_done = nullptr;                // boundary planes of the next field written
+  cudaEvent_t ev_xchg_done = nullptr;               // last halo exchange issued on s_bnd has drained
   cudaEvent_t ev_ghost_ready[2] = {nullptr, nullptr};  // ghosts of buf[p] filled
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;     // timing
   // direct halo transport: 64-bit sequence counters in THIS slab's memory, written by the
@@ -144,7 +145,8 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
                  fdb_comm* comm, int want_tma);  // want_tma: 0 none, 1 upwind, 2 7-point stencil
 void field_destroy(Field* f);
 int field_set_stream(Field* f, void* stream);
-int field_upload(Field* f, int p, const double* host_global, const double* host_slab);
+// async: no host synchronisation at all, the copy is ordered behind the handle's earlier work
+int field_upload(Field* f, int p, const double* host_global, const double* host_slab, bool async = false);
 int field_download(Field* f, int p, double* host_global, double* host_slab);
 int field_fill_delta(Field* f, int p);
 // (re)fill the ghosts of buf[p] from the neighbours' boundary planes; enqueued on
@@ -159,15 +161,17 @@ int field_sync(Field* f);
 int field_sum(Field* f, int p, double* out);
 int field_sqdev(Field* f, int p, double mean, double* out);
 
-// one sweep of a stencil kernel over every slab: boundary planes first (their
-// halos start travelling while the interior is computed), ghosts of the new
-// field exchanged, buffers not swapped.  `launch(d, ibeg, iend, stream)` must
-// enqueue the kernel computing local planes [ibeg,iend) of buf[1-cur] from buf[cur].
+// one sweep of a stencil kernel over every slab: boundary planes first (their halos start
+// travelling while the interior is computed), ghosts of the new field exchanged, buffers not
+// swapped.  `launch(f, d, X, ibeg, iend, stream)` must enqueue the kernel computing local planes
+// [ibeg,iend) of buf[1-X] from buf[X] on slab d; `depth` is set per sweep by the plan.
 struct SweepLauncher {
-  virtual int launch(Field* f, int d, int64_t ibeg, int64_t iend, cudaStream_t s) = 0;
+  virtual int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) = 0;
   virtual ~SweepLauncher() {}
 };
-int field_sweep(Field* f, SweepLauncher* L, int depth);  // depth = ghost planes the kernel reads/exchanges
+// runs the sweeps depths[0..n) back to back (each advances the field once; cur flips after
+// each).  Devices of one process are driven by one host thread each when the transport allows.
+int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n);
 
 // ---- kernels ----------------------------------------------------------------
 struct UpwindCoeffs {
@@ -176,13 +180,13 @@ struct UpwindCoeffs {
   bool active[3];
 };
 
-int launch_upwind_generic(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+int launch_upwind_generic(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                           cudaStream_t s);
 bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k);
 bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T);
-int launch_upwind_fused(Field& f, int d, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                         cudaStream_t s);
-int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                       cudaStream_t s);
 
 struct StencilBranches {
@@ -190,10 +194,10 @@ struct StencilBranches {
   int off[32][3];   // internal-axis offsets, already in application order
   double w[32];
 };
-int launch_stencil_generic(const Field& f, int d, int64_t ibeg, int64_t iend,
+int launch_stencil_generic(const Field& f, int d, int X, int64_t ibeg, int64_t iend,
                            const StencilBranches& b, cudaStream_t s);
 bool stencil_lap7_supported(const Field& f, const StencilBranches& b);
-int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const StencilBranches& b,
+int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
                         cudaStream_t s);
 
 int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode, double mean,

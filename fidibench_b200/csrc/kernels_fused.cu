@@ -373,7 +373,7 @@ static int fused_maps(const Field& f, int d, int T, const FusedConfig& C, int p,
   return FDB_OK;
 }
 
-int launch_upwind_fused(Field& f, int d, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                         cudaStream_t s) {
   if (iend <= ibeg) return FDB_OK;
   Slab& sl = f.slabs[d];
@@ -399,7 +399,7 @@ int launch_upwind_fused(Field& f, int d, int T, int64_t ibeg, int64_t iend, cons
     sl.fused_cfg = (const void*)C;
   }
   FusedArgs a;
-  a.out = f.body(d, 1 - f.cur);
+  a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];
   a.n2 = f.geo.n[2];
   a.ibeg = ibeg;
@@ -428,7 +428,7 @@ int launch_upwind_fused(Field& f, int d, int T, int64_t ibeg, int64_t iend, cons
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
   const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
-  C->kernel<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const FusedMaps*>(sl.fused_maps[f.cur]), a);
+  C->kernel<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const FusedMaps*>(sl.fused_maps[X]), a);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;

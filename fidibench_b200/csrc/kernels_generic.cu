@@ -197,15 +197,15 @@ int grid_for(int64_t work_items) {
 
 }  // namespace
 
-int launch_upwind_generic(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+int launch_upwind_generic(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                           cudaStream_t s) {
   if (iend <= ibeg) return FDB_OK;
   const Slab& sl = f.slabs[d];
   UpwindArgs a;
-  a.body = f.body(d, f.cur);
-  a.glo = f.ghost_lo(d, f.cur);
-  a.ghi = f.ghost_hi(d, f.cur);
-  a.out = f.body(d, 1 - f.cur);
+  a.body = f.body(d, X);
+  a.glo = f.ghost_lo(d, X);
+  a.ghi = f.ghost_hi(d, X);
+  a.out = f.body(d, 1 - X);
   a.nloc = sl.nloc();
   a.n1 = f.geo.n[1];
   a.n2 = f.geo.n[2];
@@ -221,15 +221,15 @@ int launch_upwind_generic(const Field& f, int d, int64_t ibeg, int64_t iend, con
   return FDB_OK;
 }
 
-int launch_stencil_generic(const Field& f, int d, int64_t ibeg, int64_t iend,
+int launch_stencil_generic(const Field& f, int d, int X, int64_t ibeg, int64_t iend,
                            const StencilBranches& b, cudaStream_t s) {
   if (iend <= ibeg) return FDB_OK;
   const Slab& sl = f.slabs[d];
   StencilArgs a;
-  a.body = f.body(d, f.cur);
-  a.glo = f.ghost_lo(d, f.cur);
-  a.ghi = f.ghost_hi(d, f.cur);
-  a.out = f.body(d, 1 - f.cur);
+  a.body = f.body(d, X);
+  a.glo = f.ghost_lo(d, X);
+  a.ghi = f.ghost_hi(d, X);
+  a.out = f.body(d, 1 - X);
   a.nloc = sl.nloc();
   a.n1 = f.geo.n[1];
   a.n2 = f.geo.n[2];

@@ -505,7 +505,7 @@ bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k) {
   return true;
 }
 
-int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                       cudaStream_t s) {
   if (iend <= ibeg) return FDB_OK;
   const Slab& sl = f.slabs[d];
@@ -522,7 +522,7 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
     at.done = true;
   }
   UpwindTmaArgs a;
-  a.out = f.body(d, 1 - f.cur);
+  a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];
   a.n2 = f.geo.n[2];
   a.ibeg = ibeg;
@@ -551,7 +551,7 @@ int launch_upwind_tma(const Field& f, int d, int64_t ibeg, int64_t iend, const U
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
   const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
-  const int p = f.cur;
+  const int p = X;
   C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p],
                                                      sl.tm_glo[p], a);
   count_launch();
@@ -638,7 +638,7 @@ bool stencil_lap7_supported(const Field& f, const StencilBranches& b) {
   return true;
 }
 
-int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const StencilBranches& b,
+int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
                         cudaStream_t s) {
   if (iend <= ibeg) return FDB_OK;
   const Slab& sl = f.slabs[d];
@@ -655,7 +655,7 @@ int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const
     at.done = true;
   }
   Lap7Args a;
-  a.out = f.body(d, 1 - f.cur);
+  a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];
   a.n2 = f.geo.n[2];
   a.nloc = sl.nloc();
@@ -686,7 +686,7 @@ int launch_stencil_lap7(const Field& f, int d, int64_t ibeg, int64_t iend, const
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
   const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
-  const int p = f.cur;
+  const int p = X;
   C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p],
                                                      sl.tm_ghi[p], a);
   count_launch();

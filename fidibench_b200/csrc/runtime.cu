@@ -11,6 +11,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace fdb {
 
@@ -251,6 +252,7 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
     s.own_main = true;
     FDB_CUDA(cudaEventCreateWithFlags(&s.ev_local_done, cudaEventDisableTiming));
     FDB_CUDA(cudaEventCreateWithFlags(&s.ev_bnd_done, cudaEventDisableTiming));
+    FDB_CUDA(cudaEventCreateWithFlags(&s.ev_xchg_done, cudaEventDisableTiming));
     FDB_CUDA(cudaEventCreateWithFlags(&s.ev_ghost_ready[0], cudaEventDisableTiming));
     FDB_CUDA(cudaEventCreateWithFlags(&s.ev_ghost_ready[1], cudaEventDisableTiming));
     FDB_CUDA(cudaEventCreate(&s.ev_t0));
@@ -259,6 +261,7 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
     FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
     FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[0], s.s_bnd));
     FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[1], s.s_bnd));
+    FDB_CUDA(cudaEventRecord(s.ev_xchg_done, s.s_bnd));
   }
   // peer access between neighbouring devices of this process
   if (!comm && f->ngpus > 1) {
@@ -332,7 +335,7 @@ void field_destroy(Field* f) {
     if (s.plane_sums) cudaFree(s.plane_sums);
     if (s.s_main && s.own_main) cudaStreamDestroy(s.s_main);
     if (s.s_bnd) cudaStreamDestroy(s.s_bnd);
-    for (cudaEvent_t ev : {s.ev_local_done, s.ev_bnd_done, s.ev_ghost_ready[0], s.ev_ghost_ready[1],
+    for (cudaEvent_t ev : {s.ev_local_done, s.ev_bnd_done, s.ev_xchg_done, s.ev_ghost_ready[0], s.ev_ghost_ready[1],
                            s.ev_t0, s.ev_t1})
       if (ev) cudaEventDestroy(ev);
   }
@@ -394,12 +397,14 @@ static int field_publish(Field* f, int p) {
   return field_ack(f);
 }
 
-int field_upload(Field* f, int p, const double* host_global, const double* host_slab) {
-  FDB_TRY(field_sync(f));
+int field_upload(Field* f, int p, const double* host_global, const double* host_slab, bool async) {
+  if (!async) FDB_TRY(field_sync(f));
   const int64_t plane = f->geo.plane();
   for (int d = 0; d < f->ngpus; ++d) {
     Slab& s = f->slabs[d];
     FDB_CUDA(cudaSetDevice(s.device));
+    // the last halo exchange may still be reading this buffer's boundary planes on s_bnd
+    FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_xchg_done, 0));
     const double* src = host_global ? host_global + s.lo * plane
                                     : host_slab + (s.lo - f->slabs[0].lo) * plane;
     FDB_CUDA(cudaMemcpyAsync(f->body(d, p), src, (size_t)(s.nloc() * plane) * sizeof(double),
@@ -469,6 +474,7 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
                                  cudaMemcpyDeviceToDevice, s.s_bnd));
         FDB_TRY(stream_write(s.s_bnd, &s.nbr_flags[NBR_PREV][F_GHOST_HI], e));
       }
+      FDB_CUDA(cudaEventRecord(s.ev_xchg_done, s.s_bnd));
       f->last_halo_bytes += (double)bytes * ((f->need_lo ? 1 : 0) + (f->need_hi ? 1 : 0));
     }
     f->ghost_seq[p] = e;
@@ -495,6 +501,7 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
     FDB_NCCL(ncclGroupEnd());
     count_launch();
     FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[p], s.s_bnd));
+    FDB_CUDA(cudaEventRecord(s.ev_xchg_done, s.s_bnd));
     f->last_halo_bytes += (double)bytes * ((f->need_lo ? 1 : 0) + (f->need_hi ? 1 : 0));
     return FDB_OK;
   }
@@ -521,66 +528,164 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
                                    s.s_bnd));
     }
     FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[p], s.s_bnd));
+    FDB_CUDA(cudaEventRecord(s.ev_xchg_done, s.s_bnd));
     f->last_halo_bytes += (double)bytes * ((f->need_lo ? 1 : 0) + (f->need_hi ? 1 : 0));
   }
   return FDB_OK;
 }
 
-// One sweep: buf[cur] -> buf[1-cur] on every slab (see fdb_internal.h).
-int field_sweep(Field* f, SweepLauncher* L, int depth) {
-  const int X = f->cur, Y = 1 - X;
-  if (f->single()) {
-    Slab& s = f->slabs[0];
-    FDB_CUDA(cudaSetDevice(s.device));
-    FDB_TRY(L->launch(f, 0, 0, s.nloc(), s.s_main));
-    return FDB_OK;
+// ---- sweeps ----------------------------------------------------------------------------------
+// Boundary/interior split of a slab for ghost depth `depth`.
+static void split_slab(const Field* f, int64_t nloc, int depth, int64_t* b_end, int64_t* t_beg) {
+  *b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
+  *t_beg = f->need_lo ? (nloc - depth > *b_end ? nloc - depth : *b_end) : nloc;
+}
+
+// Direct transport, one slab, one sweep: everything this device has to enqueue for the sweep
+// that reads buf[X] (ghosts from exchange `gseq`) and performs exchange `e` into the
+// neighbours' ghosts of buf[Y].  Touches no shared host state, so the devices of one process
+// can be driven by independent host threads.
+static int sweep_device_direct(Field* f, int d, SweepLauncher* L, int depth, int X, uint64_t gseq, uint64_t e,
+                               double* halo_bytes) {
+  const int Y = 1 - X;
+  Slab& s = f->slabs[d];
+  const int64_t plane = f->geo.plane();
+  const int64_t nloc = s.nloc();
+  const size_t bytes = (size_t)depth * (size_t)plane * sizeof(double);
+  const int64_t lo_skip = (int64_t)(f->G - depth) * plane;
+  int64_t b_end, t_beg;
+  split_slab(f, nloc, depth, &b_end, &t_beg);
+  // 1. boundary planes on the high-priority stream
+  FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
+  if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_LO], gseq));
+  if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_HI], gseq));
+  FDB_TRY(L->launch(f, d, X, depth, 0, b_end, s.s_bnd));
+  FDB_TRY(L->launch(f, d, X, depth, t_beg, nloc, s.s_bnd));
+  FDB_CUDA(cudaEventRecord(s.ev_bnd_done, s.s_bnd));
+  // 2. push them into the neighbours' ghost planes (copy engines), bump their counters
+  if (f->need_lo) {
+    FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_ACK_NEXT], e - 1));
+    FDB_CUDA(cudaMemcpyAsync(s.nbr_buf[NBR_NEXT][Y] + lo_skip, f->body(d, Y) + (nloc - depth) * plane, bytes,
+                             cudaMemcpyDeviceToDevice, s.s_bnd));
+    FDB_TRY(stream_write(s.s_bnd, &s.nbr_flags[NBR_NEXT][F_GHOST_LO], e));
+    *halo_bytes += (double)bytes;
   }
-  // 1. boundary planes (the ones a neighbour needs) on the high-priority stream
+  if (f->need_hi) {
+    FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_ACK_PREV], e - 1));
+    FDB_CUDA(cudaMemcpyAsync(s.nbr_buf[NBR_PREV][Y] + (int64_t)(f->G + nloc) * plane, f->body(d, Y), bytes,
+                             cudaMemcpyDeviceToDevice, s.s_bnd));
+    FDB_TRY(stream_write(s.s_bnd, &s.nbr_flags[NBR_PREV][F_GHOST_HI], e));
+    *halo_bytes += (double)bytes;
+  }
+  FDB_CUDA(cudaEventRecord(s.ev_xchg_done, s.s_bnd));
+  // 3. interior on the main stream, overlapped with the transfer
+  if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_main, &s.flags[F_GHOST_LO], gseq));
+  if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_main, &s.flags[F_GHOST_HI], gseq));
+  FDB_TRY(L->launch(f, d, X, depth, b_end, t_beg, s.s_main));
+  FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_bnd_done, 0));
+  FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
+  // 4. this round is complete here: the producers of this slab's ghosts may overwrite them
+  if (f->need_lo) FDB_TRY(stream_write(s.s_main, &s.nbr_flags[NBR_PREV][F_ACK_NEXT], e));
+  if (f->need_hi) FDB_TRY(stream_write(s.s_main, &s.nbr_flags[NBR_NEXT][F_ACK_PREV], e));
+  return FDB_OK;
+}
+
+// Legacy transports (NCCL send/recv between processes, event-ordered peer copies in one
+// process): one sweep over every slab, driven by the calling thread.
+static int field_sweep_legacy(Field* f, SweepLauncher* L, int depth) {
+  const int X = f->cur, Y = 1 - X;
   for (int d = 0; d < f->ngpus; ++d) {
     Slab& s = f->slabs[d];
     FDB_CUDA(cudaSetDevice(s.device));
-    const int64_t nloc = s.nloc();
-    const int64_t b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
-    const int64_t t_beg = f->need_lo ? (nloc - depth > b_end ? nloc - depth : b_end) : nloc;
+    int64_t b_end, t_beg;
+    split_slab(f, s.nloc(), depth, &b_end, &t_beg);
     FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
-    if (f->direct) {
-      if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_LO], f->ghost_seq[X]));
-      if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_HI], f->ghost_seq[X]));
-    } else {
-      FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_ghost_ready[X], 0));
-    }
-    if (!f->comm && !f->direct) {
-      // WAR on the planes about to be rewritten: the neighbours' last pull of
-      // them (two sweeps ago, same buffer) must have finished.  NCCL sends are
-      // ordered by s_bnd itself.
+    FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_ghost_ready[X], 0));
+    if (!f->comm) {
+      // WAR on the planes about to be rewritten: the neighbours' last pull of them (two
+      // sweeps ago, same buffer) must have finished.  NCCL sends are ordered by s_bnd itself.
       const int g = f->ngpus;
       if (f->need_lo) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[(d + 1) % g].ev_ghost_ready[Y], 0));
       if (f->need_hi) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[(d + g - 1) % g].ev_ghost_ready[Y], 0));
     }
-    FDB_TRY(L->launch(f, d, 0, b_end, s.s_bnd));
-    FDB_TRY(L->launch(f, d, t_beg, nloc, s.s_bnd));
+    FDB_TRY(L->launch(f, d, X, depth, 0, b_end, s.s_bnd));
+    FDB_TRY(L->launch(f, d, X, depth, t_beg, s.nloc(), s.s_bnd));
     FDB_CUDA(cudaEventRecord(s.ev_bnd_done, s.s_bnd));
   }
-  // 2. their halos start travelling
   FDB_TRY(field_exchange(f, Y, /*after_bnd=*/true, depth));
-  // 3. interior, overlapped with the exchange
   for (int d = 0; d < f->ngpus; ++d) {
     Slab& s = f->slabs[d];
     FDB_CUDA(cudaSetDevice(s.device));
-    const int64_t nloc = s.nloc();
-    const int64_t b_end = f->need_hi ? (depth < nloc ? depth : nloc) : 0;
-    const int64_t t_beg = f->need_lo ? (nloc - depth > b_end ? nloc - depth : b_end) : nloc;
-    if (f->direct) {
-      if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_main, &s.flags[F_GHOST_LO], f->ghost_seq[X]));
-      if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_main, &s.flags[F_GHOST_HI], f->ghost_seq[X]));
-    } else {
-      FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_ghost_ready[X], 0));
-    }
-    FDB_TRY(L->launch(f, d, b_end, t_beg, s.s_main));
+    int64_t b_end, t_beg;
+    split_slab(f, s.nloc(), depth, &b_end, &t_beg);
+    FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_ghost_ready[X], 0));
+    FDB_TRY(L->launch(f, d, X, depth, b_end, t_beg, s.s_main));
     FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_bnd_done, 0));
     FDB_CUDA(cudaEventRecord(s.ev_local_done, s.s_main));
   }
-  return field_ack(f);
+  return FDB_OK;
+}
+
+int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n) {
+  if (n <= 0) return FDB_OK;
+  if (f->single()) {
+    Slab& s = f->slabs[0];
+    FDB_CUDA(cudaSetDevice(s.device));
+    for (int i = 0; i < n; ++i) {
+      FDB_TRY(L->launch(f, 0, f->cur, depths[i], 0, s.nloc(), s.s_main));
+      f->cur = 1 - f->cur;
+    }
+    return FDB_OK;
+  }
+  if (!f->direct) {
+    for (int i = 0; i < n; ++i) {
+      FDB_TRY(field_sweep_legacy(f, L, depths[i]));
+      f->cur = 1 - f->cur;
+    }
+    return FDB_OK;
+  }
+  // direct transport: the per-device enqueue sequences are independent of one another
+  const int g = f->ngpus;
+  const int X0 = f->cur;
+  const uint64_t e0 = f->xseq;
+  const uint64_t gs0 = f->ghost_seq[X0];
+  std::vector<int> rc((size_t)g, FDB_OK);
+  std::vector<double> halo((size_t)g, 0.0);
+  std::vector<std::string> err((size_t)g);
+  auto drive = [&](int d) {
+    if (cudaSetDevice(f->slabs[d].device) != cudaSuccess) {
+      rc[(size_t)d] = set_error(FDB_E_CUDA, "cudaSetDevice(%d) failed", f->slabs[d].device);
+      err[(size_t)d] = last_error();
+      return;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int X = (X0 + i) & 1;
+      // sweep i reads the ghosts of exchange e0+i (the first sweep: whatever filled buf[X0]) and
+      // performs exchange e0+i+1
+      const uint64_t gseq = (i == 0) ? gs0 : e0 + (uint64_t)i;
+      const int r = sweep_device_direct(f, d, L, depths[i], X, gseq, e0 + (uint64_t)i + 1, &halo[(size_t)d]);
+      if (r != FDB_OK) {
+        rc[(size_t)d] = r;
+        err[(size_t)d] = last_error();  // thread-local text, carried back to the caller's thread
+        return;
+      }
+    }
+  };
+  if (g == 1) {
+    drive(0);
+  } else {
+    std::vector<std::thread> threads;
+    for (int d = 0; d < g; ++d) threads.emplace_back(drive, d);
+    for (auto& t : threads) t.join();
+  }
+  for (int d = 0; d < g; ++d)
+    if (rc[(size_t)d] != FDB_OK) return set_error(rc[(size_t)d], "%s", err[(size_t)d].c_str());
+  for (int d = 0; d < g; ++d) f->last_halo_bytes += halo[(size_t)d];
+  f->xseq = e0 + (uint64_t)n;
+  f->cur = (X0 + n) & 1;
+  f->ghost_seq[f->cur] = f->xseq;                 // the last exchange filled the new current buffer
+  f->ghost_seq[1 - f->cur] = f->xseq - (n >= 1 ? 1 : 0);
+  return FDB_OK;
 }
 
 // ---- reductions -------------------------------------------------------------------------

@@ -101,6 +101,12 @@ class Upwind:
             raise ValueError(f"expected a slab of {self.slab_cells()} cells, got {a.size}")
         check(lib.fdb_upwind_set_slab(self._h, a.ctypes.data_as(C.c_void_p)))
 
+    def set_slab_async(self, slab: np.ndarray) -> None:
+        """Enqueue the upload only (keep `slab` alive and unchanged until the next sync)."""
+        if slab.dtype != np.float64 or not slab.flags["C_CONTIGUOUS"] or slab.size != self.slab_cells():
+            raise ValueError("set_slab_async needs a C-contiguous float64 array of slab_cells() elements")
+        check(lib.fdb_upwind_set_slab_async(self._h, slab.ctypes.data_as(C.c_void_p)))
+
     def slab_cells(self) -> int:
         if self.ndims == 1:
             return self.ntot

@@ -106,6 +106,11 @@ int fdb_upwind_local_range(const fdb_upwind *h, int64_t *lo, int64_t *hi);
 int fdb_upwind_set_field(fdb_upwind *h, const double *host_field);
 /* overwrite only this handle's planes [lo,hi) from a host array of that size */
 int fdb_upwind_set_slab(fdb_upwind *h, const double *host_slab);
+/* same, enqueue only: the copy is ordered behind the handle's earlier work and ahead of
+ * its later work; host_slab (pinned memory for a truly asynchronous copy) must stay valid
+ * and unchanged until the next fdb_upwind_sync/checksum/get on this handle.  Lets a caller
+ * overlap the upload of one handle with the advect of another. */
+int fdb_upwind_set_slab_async(fdb_upwind *h, const double *host_slab);
 /* reset to the ctor's initial condition (delta at cell 0), upwind.cxx:45-48 */
 int fdb_upwind_reset(fdb_upwind *h);
 
