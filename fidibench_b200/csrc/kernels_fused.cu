@@ -34,11 +34,12 @@ using namespace ptx;
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int T_, int CJ_, int R_, int STAGES_, bool SHFL_ = false>
+template <int T_, int CJ_, int R_, int STAGES_, bool SHFL_ = false, int BK_ = 128, int MINB_ = 1>
 struct FusedCfg {
   static constexpr int T = T_, CJ = CJ_, R = R_, STAGES = STAGES_;
   static constexpr bool SHFL = SHFL_;                  // k-1 neighbour by warp shuffle instead of LDS.64
-  static constexpr int BK = 128;                       // output cells per tile row
+  static constexpr int BK = BK_;                       // output cells per tile row
+  static constexpr int MINB = MINB_;                   // CTAs per SM the register budget is sized for
   static constexpr int HKC = 2 * (T / 2);              // redundant compute columns (even, >= T-1)
   static constexpr int HKI = HKC + 2;                  // input halo columns (even, >= T)
   static constexpr int CK = BK + HKC;                  // compute columns
@@ -97,7 +98,7 @@ struct FusedMaps {
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 1)
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
     upwind3d_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -302,6 +303,10 @@ const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
     make_fused<FusedCfg<3, 21, 3, 4, true>>("t3_cj21_r3_s4_shfl"),
     make_fused<FusedCfg<3, 16, 2, 4, true>>("t3_cj16_r2_s4_shfl"),
+    make_fused<FusedCfg<3, 18, 3, 4, false, 64, 2>>("t3_cj18_r3_s4_bk64_2cta"),
+    make_fused<FusedCfg<3, 18, 3, 4, true, 64, 2>>("t3_cj18_r3_s4_bk64_2cta_shfl"),
+    make_fused<FusedCfg<3, 21, 3, 3, false, 64, 2>>("t3_cj21_r3_s3_bk64_2cta"),
+    make_fused<FusedCfg<3, 21, 3, 5, true>>("t3_cj21_r3_s5_shfl"),
 };
 const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),

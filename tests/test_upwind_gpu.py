@@ -259,3 +259,16 @@ def test_fused_in_process_slabs(gpu_fb, ngpus, fuse):
         up.advect(8 * ngpus + 5, up.default_dt())
         f = up.field()
     assert np.array_equal(f, C.upwind_advect(a, 8 * ngpus + 5))
+
+
+def test_config3_1024cubed_100_steps_corner_rule(gpu_fb):
+    """BASELINE config 3 on one GPU (8 GiB per field): bitwise corner + exact zeros."""
+    g = golden("upwind_128_s100.npz")
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [1024] * 3) as up:
+        up.advect(100, up.default_dt())
+        cs = up.checksum()
+        f = up.field()
+    assert np.array_equal(f[:101, :101, :101], g["corner"])
+    assert np.count_nonzero(f[101:]) == 0 and np.count_nonzero(f[:101, 101:]) == 0 \
+        and np.count_nonzero(f[:101, :101, 101:]) == 0
+    assert cs == pytest.approx(float(g["checksum"]), rel=RTOL)
