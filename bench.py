@@ -206,14 +206,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3  # timing rule: at least 3 warm-up steps
-
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return reference_arm(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
 
     import numpy as np
     import torch

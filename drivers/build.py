@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "bin")
 LIBDIR = os.path.join(ROOT, "fidibench_b200", "lib")
-TARGETS = ["upwindCuda", "laplacianCuda", "upwindMpiCuda"]
+TARGETS = ["upwindCuda", "laplacianCuda", "upwindMpiCuda", "testStencil2dCuda"]
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 

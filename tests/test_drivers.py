@@ -104,3 +104,17 @@ def test_invalid_decomposition_message(drivers, gpu_fb):
     p = run(drivers["laplacianCuda"], "-numDims", "3", "-numCells", "33", "-ngpus", "2")
     assert "No valid domain decomposition could be found" in p.stderr
     assert "Decomposition is invalid" in p.stderr
+
+
+@pytest.mark.gpu
+def test_stencil2d_driver_prints_the_reference_values(drivers, gpu_fb):
+    """ref: laplacian/cxx/testStencil2d.cxx -- out(i,j) = in(i+1,j) - in(i,j-1), in = 1 where i*j == 0."""
+    p = run(drivers["testStencil2dCuda"])
+    assert p.returncode == 0, p.stderr
+    vals = {}
+    for m in re.finditer(r"inds = (\d+) (\d+)\s+outData = (\S+)", p.stderr):
+        vals[(int(m.group(1)), int(m.group(2)))] = float(m.group(3))
+    assert len(vals) == 64
+    f = lambda i, j: 1.0 if (i % 8) * (j % 8) == 0 else 0.0
+    for (i, j), v in vals.items():
+        assert v == f(i + 1, j) - f(i, j - 1)
