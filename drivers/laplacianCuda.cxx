@@ -19,6 +19,20 @@ static double func(const std::vector<double>& pos) {
   return res;
 }
 
+// ref: laplacian.cxx:55-65 -- 2*numDims+1 points, diagonal -2*numDims, neighbours +1, no 1/h^2 scaling
+static std::map<std::vector<int>, double> laplacianStencil(size_t numDims) {
+  std::map<std::vector<int>, double> st;
+  const std::vector<int> centre(numDims, 0);
+  st[centre] = -2.0 * numDims;
+  for (size_t axis = 0; axis < numDims; ++axis)
+    for (int side = -1; side <= 1; side += 2) {
+      std::vector<int> o(centre);
+      o[axis] = side;
+      st[o] = 1.0;
+    }
+  return st;
+}
+
 int main(int argc, char** argv) {
   CmdLineArgParser args;
   args.setPurpose("Purpose: benchmark finite difference operations.");
@@ -36,17 +50,7 @@ int main(int argc, char** argv) {
     const size_t numDims = (size_t)args.get<int>("-numDims");
     const bool writeVTK = args.get<bool>("-vtk");
 
-    // the stencil, ref: laplacian.cxx:55-65 (no 1/h^2 scaling)
-    std::map<std::vector<int>, double> stencil;
-    std::vector<int> offset(numDims, 0);
-    stencil[offset] = -2.0 * numDims;
-    for (size_t i = 0; i < numDims; ++i) {
-      offset[i] = 1;
-      stencil[offset] = 1.0;
-      offset[i] = -1;
-      stencil[offset] = 1.0;
-      offset[i] = 0;
-    }
+    const std::map<std::vector<int>, double> stencil = laplacianStencil(numDims);
 
     std::vector<size_t> globalDims(numDims, numCells);
     std::vector<double> xmins(numDims, 0.0), xmaxs(numDims, 1.0);

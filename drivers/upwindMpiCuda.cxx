@@ -18,6 +18,34 @@ static double initialCondition(const std::vector<size_t>& inds) {
   return std::accumulate(inds.begin(), inds.end(), size_t(0)) == 0 ? 1.0 : 0.0;
 }
 
+// ref: upwindMpi.cxx:62-92 -- dt from the Courant number 0.1, then the upwind step as a stencil:
+// centre 1 - sum_i s_i dt v_i / dx_i, and s_i dt v_i / dx_i at offset -s_i along axis i
+static std::map<std::vector<int>, double> upwindStencil(size_t numCells, const std::vector<double>& v,
+                                                        const std::vector<double>& lengths) {
+  const size_t nd = v.size();
+  const double courant = 0.1;
+  std::vector<double> dx(nd);
+  std::vector<int> sign(nd);
+  double dt = std::numeric_limits<double>::max();
+  for (size_t j = 0; j < nd; ++j) {
+    dx[j] = lengths[j] / (double)numCells;
+    const double val = courant * dx[j] / v[j];
+    dt = (val < dt ? val : dt);
+    sign[j] = (v[j] > 0 ? 1 : -1);
+  }
+  std::map<std::vector<int>, double> st;
+  std::vector<int> o(nd, 0);
+  double diag = 1.0;
+  for (size_t i = 0; i < nd; ++i) diag -= sign[i] * dt * v[i] / dx[i];
+  st[o] = diag;
+  for (size_t i = 0; i < nd; ++i) {
+    o[i] = -sign[i];
+    st[o] = sign[i] * dt * v[i] / dx[i];
+    o[i] = 0;
+  }
+  return st;
+}
+
 int main(int argc, char** argv) {
   CmdLineArgParser args;
   args.setPurpose("Purpose: benchmark finite difference operations.");
@@ -35,30 +63,8 @@ int main(int argc, char** argv) {
     const size_t numSteps = (size_t)args.get<int>("-numSteps");
     const bool writeVTK = args.get<bool>("-vtk");
 
-    const std::vector<double> velocities(numDims, 1.);
-    const std::vector<double> lengths(numDims, 1.);
-    // time step and stencil weights, ref: upwindMpi.cxx:62-92
-    const double courant = 0.1;
-    std::vector<double> deltas(numDims);
-    std::vector<int> signs(numDims);
-    double dt = std::numeric_limits<double>::max();
-    for (size_t j = 0; j < numDims; ++j) {
-      const double dx = lengths[j] / (double)numCells;
-      deltas[j] = dx;
-      const double val = courant * dx / velocities[j];
-      dt = (val < dt ? val : dt);
-      signs[j] = (velocities[j] > 0 ? 1 : -1);
-    }
-    std::map<std::vector<int>, double> stencil;
-    std::vector<int> offset(numDims, 0);
-    double diag = 1.0;
-    for (size_t i = 0; i < numDims; ++i) diag -= signs[i] * dt * velocities[i] / deltas[i];
-    stencil[offset] = diag;
-    for (size_t i = 0; i < numDims; ++i) {
-      offset[i] = -signs[i];
-      stencil[offset] = signs[i] * dt * velocities[i] / deltas[i];
-      offset[i] = 0;
-    }
+    const std::vector<double> velocities(numDims, 1.), lengths(numDims, 1.);
+    const std::map<std::vector<int>, double> stencil = upwindStencil(numCells, velocities, lengths);
 
     std::vector<size_t> globalDims(numDims, numCells);
     std::vector<double> xmins(numDims, 0.0);

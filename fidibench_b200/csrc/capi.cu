@@ -40,6 +40,14 @@ struct UpwindSweep : SweepLauncher {
     return tma ? launch_upwind_tma(*f, d, X, ibeg, iend, k, s)
                : launch_upwind_generic(*f, d, X, ibeg, iend, k, s);
   }
+  // the TMA kernels can mirror their top planes into the next slab's ghost planes themselves
+  bool can_push(const Field*, int) const override { return tma; }
+  int launch_push(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s, double* peer_out,
+                  int64_t peer_from) override {
+    if (!tma) return FDB_E_STATE;
+    if (depth > 1) return launch_upwind_fused(*f, d, X, depth, ibeg, iend, k, s, peer_out, peer_from);
+    return launch_upwind_tma(*f, d, X, ibeg, iend, k, s, peer_out, peer_from);
+  }
 };
 
 struct StencilSweep : SweepLauncher {
@@ -277,14 +285,22 @@ int fdb_comm_create(int rank, int nranks, const void* id_bytes, int device, fdb_
   c->rank = rank;
   c->nranks = nranks;
   c->device = device;
-  FDB_CUDA(cudaSetDevice(device));
-  FDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  FDB_CUDA(cudaMalloc(&c->scratch, 64 * sizeof(double)));
-  c->scratch_doubles = 64;
-  if (nranks > 1) {
-    ncclUniqueId id;
-    memcpy(&id, id_bytes, sizeof(id));
-    FDB_NCCL(ncclCommInitRank(&c->nccl, nranks, id, rank));
+  auto init = [&]() -> int {
+    FDB_CUDA(cudaSetDevice(device));
+    FDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FDB_CUDA(cudaMalloc(&c->scratch, 64 * sizeof(double)));
+    c->scratch_doubles = 64;
+    if (nranks > 1) {
+      ncclUniqueId id;
+      memcpy(&id, id_bytes, sizeof(id));
+      FDB_NCCL(ncclCommInitRank(&c->nccl, nranks, id, rank));
+    }
+    return FDB_OK;
+  };
+  const int rc = init();
+  if (rc != FDB_OK) {
+    fdb_comm_destroy(c);  // releases whatever was created
+    return rc;
   }
   *out = c;
   return FDB_OK;

@@ -130,6 +130,7 @@ struct Field {
   std::vector<Slab> slabs;
   int cur = 0;              // buf[cur] holds the current field
   bool direct = true;       // halo transport: peer copies + stream flags (else NCCL / event-ordered copies)
+  bool push_stores = true;  // direct transport: boundary kernels store into the neighbour's ghosts themselves
   uint64_t xseq = 0;        // halo exchanges issued so far (same on every rank)
   uint64_t ghost_seq[2] = {0, 0};  // the exchange that filled the ghosts of buf[p]
   bool ghosts_valid = false;
@@ -167,6 +168,14 @@ int field_sqdev(Field* f, int p, double mean, double* out);
 // [ibeg,iend) of buf[1-X] from buf[X] on slab d; `depth` is set per sweep by the plan.
 struct SweepLauncher {
   virtual int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) = 0;
+  // Fused halo push: same as launch(), and the kernel also stores local planes >= peer_from through
+  // `peer_out` (the next slab's ghost planes, peer-mapped).  Launchers that cannot do it return
+  // FDB_E_STATE without launching and the runtime falls back to a copy-engine transfer.
+  virtual int launch_push(Field*, int, int, int, int64_t, int64_t, cudaStream_t, double* /*peer_out*/,
+                          int64_t /*peer_from*/) {
+    return FDB_E_STATE;
+  }
+  virtual bool can_push(const Field*, int /*depth*/) const { return false; }
   virtual ~SweepLauncher() {}
 };
 // runs the sweeps depths[0..n) back to back (each advances the field once; cur flips after
@@ -185,9 +194,10 @@ int launch_upwind_generic(const Field& f, int d, int X, int64_t ibeg, int64_t ie
 bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k);
 bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T);
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                        cudaStream_t s);
+                        cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0);
+// peer_out/peer_from: planes >= peer_from are also stored into the next slab's ghost planes
 int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                      cudaStream_t s);
+                      cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0);
 
 struct StencilBranches {
   int nbranch = 0;

@@ -78,6 +78,10 @@ struct FusedArgs {
   int64_t nwork;
   int G;  // planes in the ghost tensor; local plane p < 0 is its plane G + p
   double c0, c1, c2;
+  // fused halo push: output planes p >= peer_from are ALSO stored through `peer_out`, the next
+  // slab's ghost planes mapped into this GPU's address space (NVLink peer stores); null = off
+  double* peer_out;
+  int64_t peer_from;
 };
 
 // one upwind update of a cell (ref: upwind.cxx:72-80)
@@ -235,10 +239,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
         if (s == C::T - 1) {
           if (p >= i0 && store_cols) {
             double* orow = a.out + (p * a.n1 + j) * a.n2 + k;
+            double* prow = (a.peer_out != nullptr && p >= a.peer_from)
+                               ? a.peer_out + ((p - a.peer_from) * a.n1 + j) * a.n2 + k
+                               : nullptr;
 #pragma unroll
             for (int r = 0; r < C::R; ++r) {
               const int64_t jr = j + r;
-              if (q0 + r >= C::T - 1 && jr < a.n1) st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+              if (q0 + r >= C::T - 1 && jr < a.n1) {
+                st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+                if (prow) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+              }
             }
           }
         } else {
@@ -379,7 +389,7 @@ static int fused_maps(const Field& f, int d, int T, const FusedConfig& C, int p,
 }
 
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                        cudaStream_t s) {
+                        cudaStream_t s, double* peer_out, int64_t peer_from) {
   if (iend <= ibeg) return FDB_OK;
   Slab& sl = f.slabs[d];
   FusedAttr& at = g_fused_attr[sl.device & 15][T];
@@ -415,6 +425,8 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   a.c0 = k.c[0];
   a.c1 = k.c[1];
   a.c2 = k.c[2];
+  a.peer_out = peer_out;
+  a.peer_from = peer_from;
   // The direct halo transport runs on copy engines and needs no SM.  With the NCCL transport
   // the send/recv kernels must find free SMs while the persistent interior kernel runs:
   // FDB_COMM_SMS leaves some unoccupied (mind the extra round a smaller grid can cost).

@@ -62,6 +62,8 @@ struct UpwindTmaArgs {
   int64_t nwork;        // work items
   int G;                // ghost depth of the ghost tensor (its last plane is local plane -1)
   double c0, c1, c2;
+  double* peer_out;     // next slab's ghost planes (peer-mapped) for planes >= peer_from; null = off
+  int64_t peer_from;
 };
 
 // Tensor maps of the input field, by box shape:
@@ -198,7 +200,11 @@ __global__ void __launch_bounds__(C::THREADS)
         y = __dsub_rn(y, __dmul_rn(c0, __dsub_rn(below[r].y, ctr[r].y)));
         y = __dsub_rn(y, __dmul_rn(c1, __dsub_rn(jm.y, ctr[r].y)));
         y = __dsub_rn(y, __dmul_rn(c2, __dsub_rn(ctr[r].x, ctr[r].y)));
-        if (k_ok && (j + r) < a.n1) st_global_v2(orow + (int64_t)r * a.n2, x, y);
+        if (k_ok && (j + r) < a.n1) {
+          st_global_v2(orow + (int64_t)r * a.n2, x, y);
+          if (a.peer_out != nullptr && i >= a.peer_from)
+            st_global_v2(a.peer_out + (((i - a.peer_from) * a.n1 + j + r) * a.n2 + k), x, y);
+        }
         below[r] = ctr[r];
       }
     }
@@ -506,7 +512,7 @@ bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k) {
 }
 
 int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                      cudaStream_t s) {
+                      cudaStream_t s, double* peer_out, int64_t peer_from) {
   if (iend <= ibeg) return FDB_OK;
   const Slab& sl = f.slabs[d];
   const UpwindTmaConfig& C = kUpCfgs[sl.tma_cfg];
@@ -533,6 +539,8 @@ int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, 
   a.c0 = k.c[0];
   a.c1 = k.c[1];
   a.c2 = k.c[2];
+  a.peer_out = peer_out;
+  a.peer_from = peer_from;
   // i-chunk: long enough to amortise the extra plane each work item reads,
   // short enough that every CTA gets several items (static round-robin).
   const int reserve = f.single() ? 0 : env_int("FDB_COMM_SMS", 0);  // SMs left free for NCCL halo kernels (see kernels_fused.cu)

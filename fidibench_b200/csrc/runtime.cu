@@ -284,6 +284,7 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
   // halo transport
   const char* halo_env = getenv("FDB_HALO");
   f->direct = !(halo_env && strcmp(halo_env, "nccl") == 0) && stream_memops_available();
+  f->push_stores = !(halo_env && strcmp(halo_env, "copy") == 0);  // FDB_HALO=copy: copy engines only
   if (f->nparts > 1 && f->direct) {
     if (comm) {
       int rc = field_open_neighbours_ipc(f);
@@ -560,13 +561,24 @@ static int sweep_device_direct(Field* f, int d, SweepLauncher* L, int depth, int
   if (f->need_lo) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_LO], gseq));
   if (f->need_hi) FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_GHOST_HI], gseq));
   FDB_TRY(L->launch(f, d, X, depth, 0, b_end, s.s_bnd));
-  FDB_TRY(L->launch(f, d, X, depth, t_beg, nloc, s.s_bnd));
-  FDB_CUDA(cudaEventRecord(s.ev_bnd_done, s.s_bnd));
-  // 2. push them into the neighbours' ghost planes (copy engines), bump their counters
-  if (f->need_lo) {
+  // Fused compute + halo push: when the kernel can, the top planes are stored straight into the
+  // next slab's ghost planes over NVLink by the boundary kernel itself (peer stores), tile by
+  // tile, instead of a copy afterwards.  The WAR wait on the neighbour's ACK then precedes it.
+  const bool push = f->need_lo && f->push_stores && t_beg == nloc - depth && L->can_push(f, depth);
+  if (push) {
     FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_ACK_NEXT], e - 1));
-    FDB_CUDA(cudaMemcpyAsync(s.nbr_buf[NBR_NEXT][Y] + lo_skip, f->body(d, Y) + (nloc - depth) * plane, bytes,
-                             cudaMemcpyDeviceToDevice, s.s_bnd));
+    FDB_TRY(L->launch_push(f, d, X, depth, t_beg, nloc, s.s_bnd, s.nbr_buf[NBR_NEXT][Y] + lo_skip, t_beg));
+  } else {
+    FDB_TRY(L->launch(f, d, X, depth, t_beg, nloc, s.s_bnd));
+  }
+  FDB_CUDA(cudaEventRecord(s.ev_bnd_done, s.s_bnd));
+  // 2. hand the boundary planes to the neighbours and bump their counters
+  if (f->need_lo) {
+    if (!push) {
+      FDB_TRY(stream_wait_geq(s.s_bnd, &s.flags[F_ACK_NEXT], e - 1));
+      FDB_CUDA(cudaMemcpyAsync(s.nbr_buf[NBR_NEXT][Y] + lo_skip, f->body(d, Y) + (nloc - depth) * plane, bytes,
+                               cudaMemcpyDeviceToDevice, s.s_bnd));
+    }
     FDB_TRY(stream_write(s.s_bnd, &s.nbr_flags[NBR_NEXT][F_GHOST_LO], e));
     *halo_bytes += (double)bytes;
   }

@@ -104,6 +104,35 @@ class Filter:
             raise ValueError("field has the wrong size")
         check(lib.fdb_stencil_set_input(self._h, a.ctypes.data_as(C.c_void_p), layout))
 
+    def set_input_slab(self, slab: np.ndarray) -> None:
+        """Only this handle's planes [lo,hi) (one-process-per-GPU runs on grids too big for one host array)."""
+        a = np.ascontiguousarray(slab, dtype=np.float64)
+        check(lib.fdb_stencil_set_input_slab(self._h, a.ctypes.data_as(C.c_void_p)))
+
+    def saveVTK(self, filename: str) -> None:
+        """ASCII structured-grid dump of the output data, layout of cxx/writeVTK.cpp:12-95."""
+        nd = self.ndims
+        if nd > 3:
+            sys.stderr.write("WARNING: writeVTK does not support more than 3 dimensions\n")
+            return
+        field = self.get(_lib.FDB_OUTPUT).reshape(-1, order="C").reshape(self.globalDims).reshape(-1, order="F")
+        cells = list(self.globalDims) + [1] * (3 - nd)
+        lo = self.xmins + [0.0] * (3 - nd)
+        hi = self.xmaxs + [1.0] * (3 - nd)
+        nodes = [cells[a] + 1 if a < nd else 2 for a in range(3)]
+        with open(filename, "w") as fh:
+            fh.write("# vtk DataFile Version 2.0\nproduced by laplacian\nASCII\nDATASET STRUCTURED_GRID\n")
+            fh.write(f"DIMENSIONS {nodes[0]} {nodes[1]} {nodes[2]}\nPOINTS {nodes[0] * nodes[1] * nodes[2]} float\n")
+            for k in range(nodes[2]):
+                for j in range(nodes[1]):
+                    for i in range(nodes[0]):
+                        x = lo[0] + (hi[0] - lo[0]) * i / float(cells[0])
+                        y = lo[1] + (hi[1] - lo[1]) * j / float(cells[1])
+                        z = lo[2] + (hi[2] - lo[2]) * k / float(cells[2])
+                        fh.write(f"{x:g} {y:g} {z:g}\n")
+            fh.write(f"CELL_DATA {cells[0] * cells[1] * cells[2]}\nSCALARS outData float\nLOOKUP_TABLE default\n")
+            fh.write("".join(f"{v:g}\n" for v in field))
+
     def iterate(self, niter: int) -> None:
         """niter x { applyFilter(); copyOutToIn() } (ref: laplacian.cxx:86-90)."""
         check(lib.fdb_stencil_iterate(self._h, int(niter)))
