@@ -16,6 +16,15 @@ TARGETS = ["upwindCuda", "laplacianCuda", "upwindMpiCuda", "testStencil2dCuda"]
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
+def _digest(paths) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for p in paths:
+        with open(p, "rb") as fh:
+            h.update(os.path.basename(p).encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> list[str]:
     from fidibench_b200 import build as fbuild
     fbuild.build()
@@ -26,13 +35,16 @@ def build(force: bool = False) -> list[str]:
     for t in TARGETS:
         src, out = os.path.join(HERE, t + ".cxx"), os.path.join(BIN, t)
         outs.append(out)
-        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out)
-                                                     for d in [src] + headers):
+        stamp = out + ".srchash"
+        digest = _digest([src] + headers)
+        if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
             continue
         cmd = [CXX, "-std=c++11", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", HERE, src,
                "-o", out, "-L", LIBDIR, "-lfidib200", "-Wl,-rpath,$ORIGIN/../../fidibench_b200/lib",
                "-Wl,--allow-shlib-undefined"]
         subprocess.run(cmd, check=True)
+        with open(stamp, "w") as fh:
+            fh.write(digest + "\n")
     return outs
 
 

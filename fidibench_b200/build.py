@@ -44,12 +44,25 @@ def host_compiler_args() -> list[str]:
     return []
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive snapshots)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        with open(path, "rb") as fh:
+            h.update(os.path.basename(path).encode() + b"\0" + fh.read())
+    h.update(" ".join(NVCC_FLAGS).replace(ROOT, "").encode())
+    return h.hexdigest()
+
+
 def stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -80,6 +93,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed, see fidibench_b200/build/nvcc.log")
     link = [cc] + host_compiler_args() + ARCH + ["-shared", "-o", LIB] + objs + ["-lnccl"]
     subprocess.run(link, check=True)
+    with open(STAMP, "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB
 
 

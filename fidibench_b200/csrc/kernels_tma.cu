@@ -251,8 +251,15 @@ struct Lap7Args {
   int G;
   double w[7];
   int has[7];  // branch present in the stencil map (absent branches are skipped, not added as 0)
+  int one[7];  // weight is exactly 1.0
   int skip_lo, skip_hi;  // no (-1,0,0) / (1,0,0) branch: the planes outside a chunk are not even loaded
 };
+
+// acc + w*v, both operations rounded separately.  (Skipping the multiply for w == 1.0 is exact but
+// the per-branch select cost 35 % on a B200 -- measured, profiles/r01g_lap7_ab.txt -- so it multiplies.)
+__device__ __forceinline__ double acc_branch(double acc, double w, int /*one*/, double v) {
+  return __dadd_rn(acc, __dmul_rn(w, v));
+}
 
 // acc = 0; for each present branch in order: acc = acc + w * in[...]   (ref: Filter.cpp:247-251)
 // The last branch (i+1) arrives one plane later, so the first six are accumulated when
@@ -369,8 +376,8 @@ __global__ void __launch_bounds__(C::THREADS)
       for (int r = 0; r < C::R; ++r) {
         double x = partial[r].x, y = partial[r].y;
         if (a.has[6]) {
-          x = __dadd_rn(x, __dmul_rn(a.w[6], above[r].x));
-          y = __dadd_rn(y, __dmul_rn(a.w[6], above[r].y));
+          x = acc_branch(x, a.w[6], a.one[6], above[r].x);
+          y = acc_branch(y, a.w[6], a.one[6], above[r].y);
         }
         st_global_v2(orow + (int64_t)r * a.n2, x, y);
       }
@@ -404,12 +411,12 @@ __global__ void __launch_bounds__(C::THREADS)
         const double2 jm = (r == 0) ? up : ctr[r - 1];
         const double2 jp = (r == C::R - 1) ? dn : ctr[r + 1];
         double x = 0.0, y = 0.0;
-        if (a.has[0]) { x = __dadd_rn(x, __dmul_rn(a.w[0], below[r].x)); y = __dadd_rn(y, __dmul_rn(a.w[0], below[r].y)); }
-        if (a.has[1]) { x = __dadd_rn(x, __dmul_rn(a.w[1], jm.x));       y = __dadd_rn(y, __dmul_rn(a.w[1], jm.y)); }
-        if (a.has[2]) { x = __dadd_rn(x, __dmul_rn(a.w[2], km1[r]));     y = __dadd_rn(y, __dmul_rn(a.w[2], ctr[r].x)); }
-        if (a.has[3]) { x = __dadd_rn(x, __dmul_rn(a.w[3], ctr[r].x));   y = __dadd_rn(y, __dmul_rn(a.w[3], ctr[r].y)); }
-        if (a.has[4]) { x = __dadd_rn(x, __dmul_rn(a.w[4], ctr[r].y));   y = __dadd_rn(y, __dmul_rn(a.w[4], kp1[r])); }
-        if (a.has[5]) { x = __dadd_rn(x, __dmul_rn(a.w[5], jp.x));       y = __dadd_rn(y, __dmul_rn(a.w[5], jp.y)); }
+        if (a.has[0]) { x = acc_branch(x, a.w[0], a.one[0], below[r].x); y = acc_branch(y, a.w[0], a.one[0], below[r].y); }
+        if (a.has[1]) { x = acc_branch(x, a.w[1], a.one[1], jm.x); y = acc_branch(y, a.w[1], a.one[1], jm.y); }
+        if (a.has[2]) { x = acc_branch(x, a.w[2], a.one[2], km1[r]); y = acc_branch(y, a.w[2], a.one[2], ctr[r].x); }
+        if (a.has[3]) { x = acc_branch(x, a.w[3], a.one[3], ctr[r].x); y = acc_branch(y, a.w[3], a.one[3], ctr[r].y); }
+        if (a.has[4]) { x = acc_branch(x, a.w[4], a.one[4], ctr[r].y); y = acc_branch(y, a.w[4], a.one[4], kp1[r]); }
+        if (a.has[5]) { x = acc_branch(x, a.w[5], a.one[5], jp.x); y = acc_branch(y, a.w[5], a.one[5], jp.y); }
         partial[r].x = x;
         partial[r].y = y;
         below[r] = ctr[r];
@@ -586,6 +593,13 @@ const Lap7Config kLapCfgs[] = {
     make_lap_cfg<Lap7Cfg<32, 128, 8, 3>>("bj32_bk128_r8_s3"),
     make_lap_cfg<Lap7Cfg<16, 64, 4, 6>>("bj16_bk64_r4_s6"),
     make_lap_cfg<Lap7Cfg<8, 32, 4, 6>>("bj8_bk32_r4_s6"),
+    make_lap_cfg<Lap7Cfg<16, 128, 4, 6>>("bj16_bk128_r4_s6"),
+    make_lap_cfg<Lap7Cfg<16, 128, 4, 8>>("bj16_bk128_r4_s8"),
+    make_lap_cfg<Lap7Cfg<16, 128, 2, 6>>("bj16_bk128_r2_s6"),
+    make_lap_cfg<Lap7Cfg<32, 128, 4, 4>>("bj32_bk128_r4_s4"),
+    make_lap_cfg<Lap7Cfg<8, 128, 4, 8>>("bj8_bk128_r4_s8"),
+    make_lap_cfg<Lap7Cfg<16, 128, 8, 5>>("bj16_bk128_r8_s5"),
+    make_lap_cfg<Lap7Cfg<32, 128, 2, 3>>("bj32_bk128_r2_s3"),
 };
 constexpr int kNumLapCfgs = sizeof(kLapCfgs) / sizeof(kLapCfgs[0]);
 KernelAttr g_lap_attr[16][kNumLapCfgs];
@@ -672,11 +686,12 @@ int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend
   a.njt = (int)(a.n1 / C.BJ);
   a.nkt = (int)(a.n2 / C.BK);
   a.G = f.G;
-  for (int i = 0; i < 7; ++i) { a.w[i] = 0.0; a.has[i] = 0; }
+  for (int i = 0; i < 7; ++i) { a.w[i] = 0.0; a.has[i] = 0; a.one[i] = 0; }
   for (int i = 0; i < b.nbranch; ++i) {
     const int slot = lap7_slot(b.off[i]);
     a.w[slot] = b.w[i];
     a.has[slot] = 1;
+    a.one[slot] = (b.w[i] == 1.0) ? 1 : 0;
   }
   a.skip_lo = !a.has[0];
   a.skip_hi = !a.has[6];

@@ -22,7 +22,7 @@ for kern in ["generic"] + cfgs:
             fl.set_kernel(fb.FDB_KERNEL_GENERIC)
         if x is not None:
             fl.set_input(x)
-        for ci in ([0] if kern == "generic" else [0, 16, 32, 64]):
+        for ci in ([0] if kern == "generic" else [int(x) for x in os.environ.get("SWEEP_CIS", "0,16,32,64").split(",")]):
             os.environ["FDB_TMA_CI"] = str(ci)
             fl.iterate(5)
             best = 1e30
