@@ -616,6 +616,9 @@ int lap7_slot(const int* o) {
 int lap7_pick_cfg(const Field& f) {
   const int forced = env_int("FDB_LAP_CFG", -1);
   const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
+  // round-1 sweeps (profiles/r01g_lap7_cfg_sweep.txt): on 1024^2 planes the 8-rows-per-thread
+  // tile (index 10) is ~6 % ahead, on 512^2 planes the default 4-rows-per-thread one
+  if (forced < 0 && n1 * n2 >= 768 * 768 && n1 % kLapCfgs[10].BJ == 0 && n2 % kLapCfgs[10].BK == 0) return 10;
   for (int c = 0; c < kNumLapCfgs; ++c) {
     if (forced >= 0 && c != forced) continue;
     if (n1 % kLapCfgs[c].BJ == 0 && n2 % kLapCfgs[c].BK == 0) return c;
