@@ -95,6 +95,8 @@ _SIGS = {
     "fdb_stencil_get_slab": (i32, [vp, i32, vp]),
     "fdb_stencil_set_kernel": (i32, [vp, i32]),
     "fdb_stencil_get_kernel": (i32, [vp, p_i32]),
+    "fdb_stencil_set_fuse": (i32, [vp, i32]),
+    "fdb_stencil_get_fuse": (i32, [vp, p_i32]),
     "fdb_stencil_set_stream": (i32, [vp, vp]),
     "fdb_stencil_last_timing": (i32, [vp, p_dbl, p_dbl, p_dbl]),
     "fdb_stencil_destroy": (i32, [vp]),

@@ -27,6 +27,8 @@ struct fdb_stencil {
   int64_t dims[3] = {1, 1, 1};
   bool out_valid = false;  // buf[1-cur] holds the last apply's output
   int kernel = FDB_KERNEL_AUTO;
+  int reach = 1;           // ghost planes one apply reads: max |offset| along the slab axis
+  int fuse = 0;            // applies per sweep in iterate(): 0 = auto, 1, or 2 (fused 7-point kernel)
 };
 
 namespace {
@@ -53,7 +55,9 @@ struct UpwindSweep : SweepLauncher {
 struct StencilSweep : SweepLauncher {
   const StencilBranches* b = nullptr;
   bool fast = false;
-  int launch(Field* f, int d, int X, int /*depth*/, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+  int fused_depth = 0;  // sweeps of this ghost depth run the two-applies-per-sweep kernel (0 = never)
+  int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    if (fused_depth > 0 && depth == fused_depth) return launch_stencil_lap7_fused(*f, d, X, ibeg, iend, *b, s);
     return fast ? launch_stencil_lap7(*f, d, X, ibeg, iend, *b, s)
                 : launch_stencil_generic(*f, d, X, ibeg, iend, *b, s);
   }
@@ -193,6 +197,18 @@ int stencil_common_create(int ndims, const int64_t* dims, int nbranch, const int
     }
   }
   if (G == 0) G = 1;
+  h->reach = G;
+  {
+    // the 3-D 7-point set can run two applies per sweep, which reads two ghost planes per side
+    const int nparts = comm ? comm->nranks : (ngpus > 0 ? ngpus : 1);
+    const int64_t nloc = geo.n[0] / nparts;
+    bool full7 = (ndims == 3 && nbranch == 7 && G == 1 && nloc >= 2);
+    for (int b = 0; b < nbranch && full7; ++b) {
+      const int* o = h->br.off[b];
+      full7 = (std::abs(o[0]) + std::abs(o[1]) + std::abs(o[2]) <= 1);  // distinct offsets: exactly the 7
+    }
+    if (full7) G = 2;
+  }
   int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/2);
   if (rc == FDB_OK) rc = field_sync(&h->field);
   if (rc != FDB_OK) {
@@ -657,6 +673,27 @@ int fdb_stencil_set_kernel(fdb_stencil* h, int kernel) {
   return FDB_OK;
 }
 
+int fdb_stencil_set_fuse(fdb_stencil* h, int applies_per_sweep) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (applies_per_sweep < 0 || applies_per_sweep > 2)
+    return set_error(FDB_E_INVALID, "applies per sweep must be 1 or 2, or 0 for auto (got %d)", applies_per_sweep);
+  if (applies_per_sweep == 2 && !stencil_lap7_fused_supported(h->field, h->br))
+    return set_error(FDB_E_INVALID,
+                     "the fused kernel runs the 3-D 7-point stencil on planes of 8k x 128m cells and slabs of at "
+                     "least two planes");
+  h->fuse = applies_per_sweep;
+  return FDB_OK;
+}
+
+int fdb_stencil_get_fuse(const fdb_stencil* h, int* applies_per_sweep) {
+  if (!h || !applies_per_sweep) return set_error(FDB_E_INVALID, "null argument");
+  int kern = FDB_KERNEL_GENERIC;
+  FDB_TRY(fdb_stencil_get_kernel(h, &kern));
+  *applies_per_sweep =
+      (kern == FDB_KERNEL_TMA && h->fuse != 1 && stencil_lap7_fused_supported(h->field, h->br)) ? 2 : 1;
+  return FDB_OK;
+}
+
 int fdb_stencil_set_stream(fdb_stencil* h, void* cuda_stream) {
   FDB_GUARD_BEGIN
   if (!h) return set_error(FDB_E_INVALID, "null handle");
@@ -671,7 +708,7 @@ static int stencil_apply_async(fdb_stencil* h) {
   int kern = FDB_KERNEL_GENERIC;
   FDB_TRY(fdb_stencil_get_kernel(h, &kern));
   sw.fast = (kern == FDB_KERNEL_TMA);
-  const int depth = f->G;
+  const int depth = h->reach;
   FDB_TRY(field_run_sweeps(f, &sw, &depth, 1));
   f->cur = 1 - f->cur;  // an apply leaves `cur` on the input; the swap flips it (copyOutToIn)
   h->out_valid = true;
@@ -711,11 +748,26 @@ int fdb_stencil_iterate(fdb_stencil* h, int64_t niter) {
   if (!h) return set_error(FDB_E_INVALID, "null handle");
   if (niter < 0) return set_error(FDB_E_INVALID, "negative iteration count");
   Field* f = &h->field;
-  FDB_TRY(timing_begin(f));
-  for (int64_t it = 0; it < niter; ++it) {
-    FDB_TRY(stencil_apply_async(h));
-    FDB_TRY(stencil_swap(h));
+  StencilSweep sw;
+  sw.b = &h->br;
+  int kern = FDB_KERNEL_GENERIC;
+  FDB_TRY(fdb_stencil_get_kernel(h, &kern));
+  sw.fast = (kern == FDB_KERNEL_TMA);
+  const bool fuse = sw.fast && h->fuse != 1 && stencil_lap7_fused_supported(*f, h->br);
+  if (h->fuse == 2 && !fuse)
+    return set_error(FDB_E_STATE, "two applies per sweep were requested but the fused kernel cannot run this problem");
+  sw.fused_depth = fuse ? 2 * h->reach : 0;
+  // plan: pairs of applies in one sweep each, then the odd one
+  std::vector<int> depths;
+  for (int64_t done = 0; done < niter;) {
+    const int t = (fuse && niter - done >= 2) ? 2 : 1;
+    depths.push_back(t * h->reach);
+    done += t;
   }
+  FDB_TRY(timing_begin(f));
+  // every sweep flips `cur` onto its output, which is exactly apply + swap
+  FDB_TRY(field_run_sweeps(f, &sw, depths.data(), (int)depths.size()));
+  if (niter > 0) h->out_valid = false;
   FDB_TRY(timing_end(f));
   f->last_updates = (double)niter * (double)f->geo.total();
   FDB_TRY(field_sync(f));

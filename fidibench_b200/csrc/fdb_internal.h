@@ -115,6 +115,9 @@ struct Slab {
   alignas(64) unsigned char fused_maps[2][8 * sizeof(CUtensorMap)];
   int fused_T = 0;
   const void* fused_cfg = nullptr;
+  // fused two-apply 7-point kernel: 12 tensor maps per buffer parity, encoded on first use
+  alignas(64) unsigned char lapf_maps[2][12 * sizeof(CUtensorMap)];
+  const void* lapf_cfg = nullptr;
 };
 
 // A field decomposed in slabs over the devices this process drives, plus the
@@ -133,6 +136,7 @@ struct Field {
   bool push_stores = true;  // direct transport: boundary kernels store into the neighbour's ghosts themselves
   uint64_t xseq = 0;        // halo exchanges issued so far (same on every rank)
   uint64_t ghost_seq[2] = {0, 0};  // the exchange that filled the ghosts of buf[p]
+  int ghost_depth[2] = {0, 0};     // how many ghost planes (nearest the body) that exchange refreshed
   bool ghosts_valid = false;
   double last_ms = 0, last_updates = 0, last_halo_bytes = 0;
 
@@ -209,6 +213,11 @@ int launch_stencil_generic(const Field& f, int d, int X, int64_t ibeg, int64_t i
 bool stencil_lap7_supported(const Field& f, const StencilBranches& b);
 int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
                         cudaStream_t s);
+// two applies per sweep (kernels_lapfused.cu): buf[1-X] = stencil(stencil(buf[X])) on planes [ibeg,iend)
+bool stencil_lap7_fused_supported(const Field& f, const StencilBranches& b);
+int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
+                              cudaStream_t s);
+const char* stencil_lap7_fused_name(const Field& f);
 
 int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode, double mean,
                       double* partial, double* plane_sums, cudaStream_t s);

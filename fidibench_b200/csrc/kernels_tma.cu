@@ -631,7 +631,7 @@ int tma_encode_slab_lap7(Field* f, int d) {
   Slab& s = f->slabs[d];
   s.have_tma = false;
   const bool plane2d = f->geo.ndims == 2 && f->geo.n[0] == 1;
-  if ((f->geo.ndims != 3 && !plane2d) || f->G != 1) return FDB_OK;
+  if (f->geo.ndims != 3 && !plane2d) return FDB_OK;
   const int c = lap7_pick_cfg(*f);
   if (c < 0) return FDB_OK;
   s.tma_cfg = c;
@@ -651,7 +651,7 @@ int tma_encode_slab_lap7(Field* f, int d) {
 
 bool stencil_lap7_supported(const Field& f, const StencilBranches& b) {
   const bool plane2d = f.geo.ndims == 2 && f.geo.n[0] == 1;
-  if ((f.geo.ndims != 3 && !plane2d) || f.G != 1) return false;
+  if (f.geo.ndims != 3 && !plane2d) return false;
   if (f.slabs.empty() || !f.slabs[0].have_tma) return false;
   if (b.nbranch < 1 || b.nbranch > 7) return false;
   int seen = 0;

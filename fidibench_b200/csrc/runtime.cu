@@ -448,6 +448,7 @@ int field_fill_delta(Field* f, int p) {
 // boundary stream, so every event is recorded on the device that owns it.
 int field_exchange(Field* f, int p, bool after_bnd, int depth) {
   if (f->single()) return FDB_OK;  // ghosts alias the far planes of the same buffer
+  f->ghost_depth[p] = depth;
   const int64_t plane = f->geo.plane();
   const size_t bytes = (size_t)depth * (size_t)plane * sizeof(double);
   const int64_t gcount = (int64_t)depth * plane;
@@ -640,6 +641,16 @@ static int field_sweep_legacy(Field* f, SweepLauncher* L, int depth) {
 
 int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n) {
   if (n <= 0) return FDB_OK;
+  if (!f->single()) {
+    // A sweep of depth T reads T ghost planes and refreshes T ghost planes of its output, so a plan
+    // must not deepen on the way; and if the exchange that filled the current buffer's ghosts was
+    // shallower than the first sweep (the previous plan ended on a remainder sweep), they are
+    // refreshed to full depth first.
+    for (int i = 1; i < n; ++i)
+      if (depths[i] > depths[i - 1])
+        return set_error(FDB_E_STATE, "sweep plan deepens from %d to %d planes", depths[i - 1], depths[i]);
+    if (depths[0] > f->ghost_depth[f->cur]) FDB_TRY(field_publish(f, f->cur));
+  }
   if (f->single()) {
     Slab& s = f->slabs[0];
     FDB_CUDA(cudaSetDevice(s.device));
@@ -697,6 +708,7 @@ int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n) {
   f->cur = (X0 + n) & 1;
   f->ghost_seq[f->cur] = f->xseq;                 // the last exchange filled the new current buffer
   f->ghost_seq[1 - f->cur] = f->xseq - (n >= 1 ? 1 : 0);
+  for (int i = 0; i < n; ++i) f->ghost_depth[(X0 + i + 1) & 1] = depths[i];
   return FDB_OK;
 }
 

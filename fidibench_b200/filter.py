@@ -150,6 +150,15 @@ class Filter:
         check(lib.fdb_stencil_get_kernel(self._h, C.byref(k)))
         return int(k.value)
 
+    def set_fuse(self, applies_per_sweep: int) -> None:
+        """Applies fused per sweep by iterate(): 1, 2 (3-D 7-point stencil, temporal blocking) or 0 = auto."""
+        check(lib.fdb_stencil_set_fuse(self._h, int(applies_per_sweep)))
+
+    def fuse(self) -> int:
+        n = C.c_int()
+        check(lib.fdb_stencil_get_fuse(self._h, C.byref(n)))
+        return int(n.value)
+
     def set_stream(self, cuda_stream: int | None) -> None:
         check(lib.fdb_stencil_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 

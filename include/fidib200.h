@@ -170,8 +170,15 @@ int fdb_stencil_apply(fdb_stencil *h);
 /* ref: Filter::copyOutToIn(), Filter.cpp:440-463 -- O(1): the buffers swap
  * roles and "output" keeps reading as the same data until the next apply */
 int fdb_stencil_swap(fdb_stencil *h);
-/* niter x { apply; swap } as laplacian.cxx:86-90, enqueued back to back */
+/* niter x { apply; swap } as laplacian.cxx:86-90, enqueued back to back.  The 3-D 7-point
+ * stencil runs two applies per sweep (temporal blocking, half the DRAM traffic) when the
+ * plane extents allow; the result is bit-identical either way. */
 int fdb_stencil_iterate(fdb_stencil *h, int64_t niter);
+/* applies fused per sweep by fdb_stencil_iterate: 1, 2, or 0 = auto (the default: 2 when the
+ * fused kernel supports the problem).  FDB_E_INVALID if 2 is asked for and cannot run. */
+int fdb_stencil_set_fuse(fdb_stencil *h, int applies_per_sweep);
+/* what the next fdb_stencil_iterate will use (1 or 2) */
+int fdb_stencil_get_fuse(const fdb_stencil *h, int *applies_per_sweep);
 /* ref: Filter::computeCheckSum("input"|"output"), Filter.cpp:465-485 */
 int fdb_stencil_checksum(fdb_stencil *h, int which, double *sum);
 int fdb_stencil_get(fdb_stencil *h, int which, double *host_field, int layout);

@@ -145,6 +145,28 @@ def gpu_main():
     assert abs(fl.computeCheckSum("output") - oracle.c.checksum(ref)) < 1e-9
     fl.close()
 
+    # two applies per sweep across ranks (ghost depth 2 on both sides), odd count, then more calls
+    b2 = rng.random((4 * world, 16, 128))
+    fl = fb.Filter(b2.shape, [0.0] * 3, [1.0] * 3, {tuple(int(x) for x in o): float(v) for o, v in zip(off, w)}, comm=comm)
+    assert fl.fuse() == 2
+    fl.set_input(b2)
+    fl.iterate(5)
+    fl.iterate(2)
+    ref = b2
+    for _ in range(7):
+        ref = oracle.c.stencil_apply(ref, off, w)
+    out = fl.get()
+    assert np.array_equal(out[fl.lo:fl.hi], ref[fl.lo:fl.hi]), f"rank {rank}: fused laplacian slab differs"
+    fl.close()
+
+    # consecutive advect calls: a call ending on a remainder sweep leaves shallow ghosts behind
+    up = fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, comm=comm)
+    up.set_field(a)
+    for n in (4, 3, 7):
+        up.advect(n, up.default_dt())
+    assert np.array_equal(up.slab(), oracle.c.upwind_advect(a, 14)[up.lo:up.hi]), f"rank {rank}: repeated advect differs"
+    up.close()
+
     dist.barrier()
     print(f"RANK {rank} OK gpu", flush=True)
     comm.close()

@@ -203,3 +203,109 @@ def test_two_d_laplacian_takes_the_tiled_kernel(gpu_fb, shape):
         ref = C.stencil_apply(ref, off, w)
     assert np.array_equal(out, ref)
     assert abs(cs - C.checksum(ref)) <= 1e-12 * max(1.0, np.abs(ref).sum())
+
+
+# ---- two applies per sweep (kernels_lapfused.cu) -----------------------------------------------------
+def _applies(a, off, w, n):
+    ref = a
+    for _ in range(n):
+        ref = C.stencil_apply(ref, off, w)
+    return ref
+
+
+@pytest.mark.parametrize("shape", [(6, 32, 256), (5, 16, 128), (2, 32, 128), (37, 48, 384), (4, 8, 128)])
+def test_fused_two_applies_bitwise(gpu_fb, shape):
+    """iterate() pairs applies into one sweep of the fused kernel (odd counts end on a single apply);
+    the field must equal the oracle's bit for bit and the unfused path's."""
+    rng = np.random.default_rng(SEED + 20)
+    a = rng.random(shape)
+    off, _ = oracle.laplacian_stencil(3)
+    w = rng.standard_normal(7)
+    with gpu_fb.Filter(shape, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        assert fl.kernel() == gpu_fb.FDB_KERNEL_TMA and fl.fuse() == 2
+        for n in (1, 2, 3, 4, 7):
+            fl.set_input(a)
+            fl.iterate(n)
+            assert np.array_equal(fl.get(), _applies(a, off, w, n)), f"{n} applies"
+        # consecutive calls carry on from the current field
+        fl.set_input(a)
+        fl.iterate(2)
+        fl.iterate(3)
+        fused = fl.get()
+        assert np.array_equal(fused, _applies(a, off, w, 5))
+        assert np.array_equal(fl.get(gpu_fb.FDB_INPUT), fused)  # copyOutToIn semantics
+        fl.set_fuse(1)
+        assert fl.fuse() == 1
+        fl.set_input(a)
+        fl.iterate(5)
+        assert np.array_equal(fl.get(), fused)
+
+
+@pytest.mark.parametrize("cfg", range(10))
+def test_fused_two_applies_every_tile_configuration(gpu_fb, cfg, monkeypatch):
+    monkeypatch.setenv("FDB_LAPF_CFG", str(cfg))
+    monkeypatch.setenv("FDB_TMA_CI", "3")  # ragged chunks of planes
+    rng = np.random.default_rng(SEED + 21)
+    a = rng.random((7, 32, 256))
+    off, w = oracle.laplacian_stencil(3)
+    with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        assert fl.fuse() == 2
+        fl.set_input(a)
+        fl.iterate(4)
+        out = fl.get()
+    assert np.array_equal(out, _applies(a, off, w, 4))
+
+
+def test_fused_laplacian_driver_sequence_128(gpu_fb):
+    """laplacian.cxx:86-90 at 128^3 through the fused kernel: 10 x (apply; copyOutToIn) from the driver's
+    input, amplified roundoff and all."""
+    off, w = oracle.laplacian_stencil(3)
+    x = C.laplacian_input([128] * 3)
+    with gpu_fb.Filter([128] * 3, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        fl.set_fuse(2)
+        fl.set_input(x)
+        fl.iterate(10)
+        y10 = fl.get()
+        launches = gpu_fb.launch_count()
+        fl.iterate(10)
+        assert gpu_fb.launch_count() - launches == 5  # five fused sweeps
+    assert np.array_equal(y10, _applies(x, off, w, 10))
+    assert np.abs(y10).max() == 1.2084444224735869e-06
+
+
+def test_fuse_falls_back_and_validates(gpu_fb):
+    off, w = oracle.laplacian_stencil(3)
+    # a plane the fused tile does not divide: auto = 1, asking for 2 is an error
+    with gpu_fb.Filter((8, 16, 64), [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        assert fl.fuse() == 1
+        with pytest.raises(gpu_fb.FdbError):
+            fl.set_fuse(2)
+        with pytest.raises(gpu_fb.FdbError):
+            fl.set_fuse(3)
+    # a 4-branch subset of the 7-point shape is not fusable
+    g = golden("upwindmpi_16.npz")
+    with gpu_fb.Filter((8, 16, 128), [0.0] * 3, [1.0] * 3, as_dict(g["offsets"], g["weights"])) as fl:
+        assert fl.fuse() == 1
+    # the generic kernel never fuses
+    with gpu_fb.Filter((8, 16, 128), [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+        fl.set_kernel(gpu_fb.FDB_KERNEL_GENERIC)
+        assert fl.fuse() == 1
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_fused_two_applies_in_process_slabs(gpu_fb, ngpus):
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(SEED + 22)
+    a = rng.random((4 * ngpus, 16, 128))
+    off, w = oracle.laplacian_stencil(3)
+    with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(off, w), ngpus=ngpus) as fl:
+        assert fl.fuse() == 2
+        fl.set_input(a)
+        fl.iterate(7)      # 2,2,2,1: ends on a one-plane exchange
+        fl.iterate(4)      # starts with a two-plane sweep: ghosts are refreshed first
+        out = fl.get()
+        fl.applyFilter()   # single apply after fused sweeps
+        out12 = fl.get()
+    assert np.array_equal(out, _applies(a, off, w, 11))
+    assert np.array_equal(out12, _applies(a, off, w, 12))

@@ -272,3 +272,20 @@ def test_config3_1024cubed_100_steps_corner_rule(gpu_fb):
     assert np.count_nonzero(f[101:]) == 0 and np.count_nonzero(f[:101, 101:]) == 0 \
         and np.count_nonzero(f[:101, :101, 101:]) == 0
     assert cs == pytest.approx(float(g["checksum"]), rel=RTOL)
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_repeated_advect_calls_on_slabs_refresh_deeper_ghosts(gpu_fb, ngpus):
+    """advect(4) ends on a one-step remainder sweep (one fresh ghost plane); the next call starts
+    with a three-step sweep that reads three -- the runtime must refresh them first."""
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(SEED + 30)
+    a = rng.random((8 * ngpus, 24, 64))
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, ngpus=ngpus) as up:
+        up.set_field(a)
+        dt = up.default_dt()
+        for n in (4, 3, 7, 1, 6):
+            up.advect(n, dt)
+        f = up.field()
+    assert np.array_equal(f, C.upwind_advect(a, 21))

@@ -1,0 +1,42 @@
+"""Fused two-apply 7-point kernel on the GPU box: python tools/sweep_lapfused.py N [cfg...]
+Prints GCUPS (cell-applies/s) for iterate() with fuse = 1 (lap7_tma_kernel) and fuse = 2 per tile
+configuration (FDB_LAPF_CFG) and plane-chunk length (FDB_TMA_CI)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fidibench_b200 as fb  # noqa: E402
+import oracle  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+cfgs = [int(x) for x in sys.argv[2:]] or list(range(10))
+cis = [int(x) for x in os.environ.get("SWEEP_CIS", "0,64").split(",")]
+ITER = 10
+off, w = oracle.laplacian_stencil(3)
+st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
+with fb.Filter([N] * 3, [0.0] * 3, [1.0] * 3, st) as fl:
+    if N <= 512:
+        fl.set_input(np.random.default_rng(3).random((N, N, N)))
+    else:  # a host array of 8 GiB is not worth the box time: one random slab, repeated
+        slab = np.random.default_rng(3).random((64, N, N))
+        fl.set_input_slab(np.concatenate([slab] * (N // 64)))
+
+    def run(tag):
+        fl.iterate(4)
+        best = 1e30
+        for _ in range(3):
+            fl.iterate(ITER)
+            best = min(best, fl.last_timing()["gpu_ms"] / ITER)
+        print(f"lap7 N={N} {tag} ms/apply={best:.4f} GCUPS={N ** 3 / best / 1e6:.1f} "
+              f"x_copy_roofline={N ** 3 * 16 / best / 1e6 / 6548.5:.3f}", flush=True)
+
+    fl.set_fuse(1)
+    run("fuse=1")
+    fl.set_fuse(2)
+    for c in cfgs:
+        os.environ["FDB_LAPF_CFG"] = str(c)
+        for ci in cis:
+            os.environ["FDB_TMA_CI"] = str(ci)
+            run(f"fuse=2 cfg={c} ci={ci}")
