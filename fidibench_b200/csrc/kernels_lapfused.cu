@@ -39,9 +39,11 @@ using namespace ptx;
 
 constexpr int lf_align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int BJ_, int R_, int STAGES_, int MINB_ = 1>
+// UNIT: the six off-centre weights are exactly 1.0 (the Laplacian, laplacian.cxx:55-65): their
+// multiplies are skipped, which is exact (1.0 * v == v for every v), so the bits do not change.
+template <int BJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1>
 struct LapFusedCfg {
-  static constexpr int BJ = BJ_, BK = 128, R = R_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int BJ = BJ_, BK = BK_, R = R_, STAGES = STAGES_, MINB = MINB_;
   static constexpr int CJ = BJ + 2;       // level-1 rows:    global j0-1 .. j0+BJ
   static constexpr int CK = BK + 4;       // level-1 columns: global k0-2 .. k0+BK+1
   static constexpr int IN_ROWS = BJ + 4;  // level-0 rows:    global j0-2 .. j0+BJ+1 (stage row s)
@@ -50,32 +52,34 @@ struct LapFusedCfg {
   static constexpr int WORKERS = TX * TY;
   static constexpr int CONSUMERS = (WORKERS + 31) / 32 * 32;
   static constexpr int CONSUMER_WARPS = CONSUMERS / 32;
-  static constexpr int THREADS = CONSUMERS + 32;
-  static constexpr int ROW_BYTES = CK * 8;
-  // Stage layout.  Three TMA boxes (2 halo rows, BJ tile rows, 2 halo rows) land back to back;
-  // every TMA destination must be 128-byte aligned, so the tile rows start at BODY_OFF and stage
-  // row s >= 2 sits ROW_SKEW bytes past s * ROW_BYTES.
-  static constexpr int BODY_OFF = lf_align128(2 * ROW_BYTES);
-  static constexpr int ROW_SKEW = BODY_OFF - 2 * ROW_BYTES;
-  static constexpr int BOT_OFF = BODY_OFF + BJ * ROW_BYTES;
-  static constexpr int MAIN_BYTES = lf_align128(BOT_OFF + 2 * ROW_BYTES);
-  // wrap-column areas: 2 cells per row (pitch 16 B), same three boxes, same skew rule
-  static constexpr int WBODY_OFF = 128;
-  static constexpr int WSKEW = WBODY_OFF - 2 * 16;
-  static constexpr int WBOT_OFF = WBODY_OFF + BJ * 16;
-  static constexpr int WRAP_BYTES = lf_align128(WBOT_OFF + 2 * 16);
-  static constexpr int WL_OFF = MAIN_BYTES;            // columns N2-2, N2-1 (left of k = 0)
-  static constexpr int WR_OFF = WL_OFF + WRAP_BYTES;   // columns 0, 1 (right of k = N2-1)
-  static constexpr int STAGE_BYTES = WR_OFF + WRAP_BYTES;
-  static constexpr int TX_MAIN = IN_ROWS * ROW_BYTES;
-  static constexpr int TX_WRAP = IN_ROWS * 16;
-  static constexpr int XP = CK * 8;                    // exchange tile row pitch
-  static constexpr int X_BYTES = lf_align128(CJ * XP);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * X_BYTES + 2 * STAGES * 8 + 128;
+  static constexpr int THREADS = CONSUMERS + 32;  // + the loader warp
+  // Stage layout: IN_ROWS rows of BKP = BK + 8 cells, global columns k0-4 .. k0+BK+3 (two
+  // unused cells on each side keep every in-row neighbour inside the row and make two rows a
+  // multiple of 128 bytes, so the three TMA boxes -- 2 halo rows, BJ tile rows, 2 halo rows --
+  // land back to back with ONE pitch).  Thread tx owns byte offset 16 + 16*tx of a row.
+  static constexpr int BKP = BK + 8;
+  static constexpr int PITCH = BKP * 8;
+  static constexpr int BODY_OFF = 2 * PITCH;
+  static constexpr int BOT_OFF = (2 + BJ) * PITCH;
+  static constexpr int MAIN_BYTES = IN_ROWS * PITCH;
+  // wrap columns of the first / last k-tile: 8-cell boxes (pitch 64 B) at columns N2-8 and 0; the
+  // loader warp copies the pair each row needs into the row's zero-filled halo cells
+  static constexpr int WPITCH = 64;
+  static constexpr int WL_OFF = lf_align128(MAIN_BYTES);
+  static constexpr int WR_OFF = WL_OFF + IN_ROWS * WPITCH;
+  static constexpr int STAGE_BYTES = WR_OFF + IN_ROWS * WPITCH;
+  static constexpr int TX_MAIN = IN_ROWS * PITCH;
+  static constexpr int TX_WRAP = IN_ROWS * WPITCH;
+  // exchange tile (level 1): same pitch and column offsets as a stage, one spare row above and
+  // below, so a thread addresses both with the same base: row q of level 1 sits at row q+1
+  static constexpr int X_BYTES = lf_align128((CJ + 2) * PITCH);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * X_BYTES + 3 * STAGES * 8 + 128;
+  static constexpr int LAG = STAGES - 2;  // planes the loader keeps in flight behind the hand-over
   static_assert(CJ % R == 0, "rows per thread must divide the level-1 tile");
-  static_assert(BJ % 8 == 0, "TMA destinations of the tile and wrap boxes must stay 128-byte aligned");
-  static_assert(BOT_OFF % 128 == 0 && WBOT_OFF % 128 == 0, "misaligned TMA destination");
-  static_assert(CK <= 256 && BJ <= 256, "TMA box limit");
+  static_assert(BJ % 2 == 0 && (2 * PITCH) % 128 == 0 && (IN_ROWS * WPITCH) % 128 == 0, "misaligned TMA destination");
+  static_assert(BKP <= 256 && BJ <= 256, "TMA box limit");
+  static_assert(IN_ROWS <= 32, "one loader lane per stage row");
+  static_assert(STAGES >= 3, "the loader needs two stages of slack");
   static_assert(THREADS <= 1024, "too many threads");
 };
 
@@ -90,29 +94,56 @@ struct LapFusedArgs {
 };
 
 // Tensor maps: m[4*t + b], t = 0 local planes, 1 ghost planes below, 2 ghost planes above;
-// box b = 0 {CK, 2} halo rows, 1 {CK, BJ} tile rows, 2 {2, 2} wrap corner, 3 {2, BJ} wrap columns
+// box b = 0 {BKP, 2} halo rows, 1 {BKP, BJ} tile rows, 2 {8, 2} wrap corner, 3 {8, BJ} wrap columns
 struct LapFusedMaps {
   CUtensorMap m[12];
 };
 
-// acc + w*v, rounded separately (ref: Filter.cpp:247-251)
+// acc + w*v, rounded separately (ref: Filter.cpp:247-251); UNIT: w is exactly 1.0
+template <bool UNIT>
 __device__ __forceinline__ double lf_acc(double acc, double w, double v) {
-  return __dadd_rn(acc, __dmul_rn(w, v));
+  return UNIT ? __dadd_rn(acc, v) : __dadd_rn(acc, __dmul_rn(w, v));
 }
 
+// position of the loader in the sequence of (work item, plane) pairs of this CTA
 template <class C>
+struct LapFusedCursor {
+  int64_t w;       // work item
+  int64_t p, i1;   // plane, end of the chunk
+  int kt, jt;
+  __device__ __forceinline__ void open(const LapFusedArgs& a) {
+    kt = (int)(w % a.nkt);
+    jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    p = i0 - 2;
+  }
+  __device__ __forceinline__ bool valid(const LapFusedArgs& a) const { return w < a.nwork; }
+  __device__ __forceinline__ void next(const LapFusedArgs& a) {
+    if (++p > i1 + 1) {
+      w += gridDim.x;
+      if (w < a.nwork) open(a);
+    }
+  }
+};
+
+template <class C, bool UNIT>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
     lap7_fused2_kernel(const __grid_constant__ LapFusedMaps maps, const LapFusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
-  const uint32_t full = xbuf + 2 * C::X_BYTES;
-  const uint32_t empty = full + C::STAGES * 8;
+  const uint32_t landed = xbuf + 2 * C::X_BYTES;      // TMA bytes of the stage have arrived
+  const uint32_t full = landed + C::STAGES * 8;       // ... and its wrap columns are in place
+  const uint32_t empty = full + C::STAGES * 8;        // every consumer warp has read the stage
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
       mbar_init(full + 8 * s, 1);
       mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
     }
@@ -121,48 +152,76 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   __syncthreads();
 
   if (warp == C::CONSUMER_WARPS) {
-    // ===================== producer warp =====================
-    if ((tid & 31) == 0) {
+    // ===================== loader warp =====================
+    // Lane 0 issues the TMA boxes of plane n; LAG planes behind, the warp waits for a plane to
+    // land, copies the periodic wrap columns of the first / last k-tile into the tile rows (one
+    // lane per row) and hands the stage to the consumers.  Issue waits for the consumers to free
+    // the stage of plane n - STAGES while planes up to n - STAGES + 1 are already handed over, so
+    // the two never wait for each other.
+    if (lane == 0) {
 #pragma unroll
       for (int m = 0; m < 12; ++m) prefetch_tmap(&maps.m[m]);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
-        const int kt = (int)(w % a.nkt);
-        const int jt = (int)((w / a.nkt) % a.njt);
-        const int64_t ic = w / ((int64_t)a.nkt * a.njt);
-        const int64_t i0 = a.ibeg + ic * a.ci;
-        const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
-        const int kb = kt * C::BK - 2;  // first level-0 column (-2 for the first k-tile: zero fill)
-        const int j0 = jt * C::BJ;
-        const int jtop = (j0 == 0) ? (int)a.n1 - 2 : j0 - 2;            // periodic rows j0-2, j0-1
-        const int jbot = (j0 + C::BJ >= (int)a.n1) ? 0 : j0 + C::BJ;    // periodic rows j0+BJ, j0+BJ+1
-        const bool first_k = (kt == 0), last_k = (kt == a.nkt - 1);
-        const uint32_t bytes = C::TX_MAIN + (first_k ? C::TX_WRAP : 0) + (last_k ? C::TX_WRAP : 0);
-        for (int64_t p = i0 - 2; p <= i1 + 1; ++p) {
-          mbar_wait(empty + 8 * stage, phase ^ 1);
-          const uint32_t st = smem + stage * C::STAGE_BYTES;
-          const uint32_t fb = full + 8 * stage;
+    }
+    LapFusedCursor<C> ci, cf;  // issue / hand-over
+    ci.w = blockIdx.x;
+    if (ci.valid(a)) ci.open(a);
+    cf = ci;
+    int si = 0, sf = 0;        // stage of the next issue / hand-over
+    uint32_t phi = 0, phf = 0;
+    int ahead = 0;             // planes issued and not yet handed over
+    while (cf.valid(a)) {
+      if (ci.valid(a)) {
+        mbar_wait(empty + 8 * si, phi ^ 1);
+        if (lane == 0) {
+          const uint32_t st = smem + si * C::STAGE_BYTES;
+          const uint32_t lb = landed + 8 * si;
+          const int kb = ci.kt * C::BK - 4;  // first stage column (negative for the first k-tile: zero fill)
+          const int j0 = ci.jt * C::BJ;
+          const int jtop = (j0 == 0) ? (int)a.n1 - 2 : j0 - 2;          // periodic rows j0-2, j0-1
+          const int jbot = (j0 + C::BJ >= (int)a.n1) ? 0 : j0 + C::BJ;  // periodic rows j0+BJ, j0+BJ+1
+          const bool first_k = (ci.kt == 0), last_k = (ci.kt == a.nkt - 1);
+          const int64_t p = ci.p;
           const int g = (p < 0) ? 4 : (p >= a.nloc ? 8 : 0);
           const int pl = (p < 0) ? a.G + (int)p : (p >= a.nloc ? (int)(p - a.nloc) : (int)p);
-          mbar_expect_tx(fb, bytes);
-          tma_load_3d(st, &maps.m[g + 0], fb, kb, jtop, pl);
-          tma_load_3d(st + C::BODY_OFF, &maps.m[g + 1], fb, kb, j0, pl);
-          tma_load_3d(st + C::BOT_OFF, &maps.m[g + 0], fb, kb, jbot, pl);
+          mbar_expect_tx(lb, C::TX_MAIN + (first_k ? C::TX_WRAP : 0) + (last_k ? C::TX_WRAP : 0));
+          tma_load_3d(st, &maps.m[g + 0], lb, kb, jtop, pl);
+          tma_load_3d(st + C::BODY_OFF, &maps.m[g + 1], lb, kb, j0, pl);
+          tma_load_3d(st + C::BOT_OFF, &maps.m[g + 0], lb, kb, jbot, pl);
           if (first_k) {
             const uint32_t wl = st + C::WL_OFF;
-            tma_load_3d(wl, &maps.m[g + 2], fb, (int)a.n2 - 2, jtop, pl);
-            tma_load_3d(wl + C::WBODY_OFF, &maps.m[g + 3], fb, (int)a.n2 - 2, j0, pl);
-            tma_load_3d(wl + C::WBOT_OFF, &maps.m[g + 2], fb, (int)a.n2 - 2, jbot, pl);
+            tma_load_3d(wl, &maps.m[g + 2], lb, (int)a.n2 - 8, jtop, pl);
+            tma_load_3d(wl + 2 * C::WPITCH, &maps.m[g + 3], lb, (int)a.n2 - 8, j0, pl);
+            tma_load_3d(wl + (2 + C::BJ) * C::WPITCH, &maps.m[g + 2], lb, (int)a.n2 - 8, jbot, pl);
           }
           if (last_k) {
             const uint32_t wr = st + C::WR_OFF;
-            tma_load_3d(wr, &maps.m[g + 2], fb, 0, jtop, pl);
-            tma_load_3d(wr + C::WBODY_OFF, &maps.m[g + 3], fb, 0, j0, pl);
-            tma_load_3d(wr + C::WBOT_OFF, &maps.m[g + 2], fb, 0, jbot, pl);
+            tma_load_3d(wr, &maps.m[g + 2], lb, 0, jtop, pl);
+            tma_load_3d(wr + 2 * C::WPITCH, &maps.m[g + 3], lb, 0, j0, pl);
+            tma_load_3d(wr + (2 + C::BJ) * C::WPITCH, &maps.m[g + 2], lb, 0, jbot, pl);
           }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        ci.next(a);
+        if (++si == C::STAGES) { si = 0; phi ^= 1; }
+        ++ahead;
+      }
+      if (ahead > C::LAG || !ci.valid(a)) {
+        mbar_wait(landed + 8 * sf, phf);
+        const uint32_t st = smem + sf * C::STAGE_BYTES;
+        if (lane < C::IN_ROWS) {
+          if (cf.kt == 0) {  // columns -2, -1 of the tile rows <- columns N2-2, N2-1
+            const double2 v = lds_v2(st + C::WL_OFF + lane * C::WPITCH + 48);
+            sts_v2(st + lane * C::PITCH + 16, v.x, v.y);
+          }
+          if (cf.kt == a.nkt - 1) {  // columns N2, N2+1 <- columns 0, 1
+            const double2 v = lds_v2(st + C::WR_OFF + lane * C::WPITCH);
+            sts_v2(st + lane * C::PITCH + C::CK * 8, v.x, v.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * sf);
+        cf.next(a);
+        if (++sf == C::STAGES) { sf = 0; phf ^= 1; }
+        --ahead;
       }
     }
     return;
@@ -174,26 +233,21 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   const int tx = wid % C::TX;
   const int ty = wid / C::TX;
   const int q0 = ty * C::R;  // first level-1 row of this thread (level-1 row q = global row j0-1+q)
-  const int lane = tid & 31;
   int stage = 0;
   uint32_t phase = 0;
   uint32_t xsel = 0;
   const double w0 = a.w[0], w1 = a.w[1], w2 = a.w[2], w3 = a.w[3], w4 = a.w[4], w5 = a.w[5], w6 = a.w[6];
-  const uint32_t cb = tx * 16;  // byte offset of this thread's pair in a tile row
-  // in-row neighbours; the outermost columns of level 1 are never used, their out-of-tile
-  // neighbours are clamped to something readable
-  const uint32_t kmb = (tx == 0) ? cb : cb - 8;
-  const uint32_t kpb = (tx == C::TX - 1) ? cb + 8 : cb + 16;
-  // exchange-tile addresses (level 1): own rows, the rows above / below (clamped at the tile edge,
-  // where the result is never used), the cells left / right
-  const uint32_t x_own = q0 * C::XP + cb;
-  const uint32_t x_up = (q0 == 0 ? 0 : q0 - 1) * C::XP + cb;
-  const uint32_t x_dn = (q0 + C::R >= C::CJ ? C::CJ - 1 : q0 + C::R) * C::XP + cb;
-  const uint32_t x_km = q0 * C::XP + kmb;
-  const uint32_t x_kp = q0 * C::XP + kpb;
-  // level-0 stage row s = level-1 row q + 1
-  auto main_row = [](int s) -> uint32_t { return s * C::ROW_BYTES + (s >= 2 ? C::ROW_SKEW : 0); };
-  auto wrap_row = [](int s) -> uint32_t { return s * 16 + (s >= 2 ? C::WSKEW : 0); };
+  // One base serves the stage (level 0: stage row s = level-1 row q + 1) and the exchange tile
+  // (level 1: row q at tile row q + 1): the row above the thread's first row, its own pair.
+  const uint32_t tb = q0 * C::PITCH + 16 + tx * 16;
+  constexpr uint32_t P = C::PITCH;
+  // rows of this thread that belong to the output tile (level-1 rows 1 .. CJ-2)
+  uint32_t rowmask = 0;
+#pragma unroll
+  for (int r = 0; r < C::R; ++r)
+    if (q0 + r >= 1 && q0 + r <= C::CJ - 2) rowmask |= 1u << r;
+  const bool store_cols = worker && tx >= 1 && tx <= C::TX - 2;
+  const int64_t plane = a.n1 * a.n2;
 
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     const int kt = (int)(w % a.nkt);
@@ -203,11 +257,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
     const int64_t k = (int64_t)kt * C::BK - 2 + 2 * tx;  // global column of this thread's first cell
     const int64_t j = (int64_t)jt * C::BJ - 1 + q0;      // global row of this thread's first row
-    const bool first_k = (kt == 0), last_k = (kt == a.nkt - 1);
-    // where level 0 of this thread's pair / left cell / right cell lives: tile rows or a wrap area
-    const bool own_wl = first_k && tx == 0, own_wr = last_k && tx == C::TX - 1;
-    const bool km_wl = first_k && tx == 1, kp_wr = last_k && tx == C::TX - 2;
-    const bool store_cols = worker && tx >= 1 && tx <= C::TX - 2;
+    // offset of (plane p-2, row j, column k) in the output, advanced by one plane per iteration
+    int64_t ooff = ((i0 - 5) * a.n1 + j) * a.n2 + k;
 
     double2 below0[C::R], part1[C::R], below1[C::R], part2[C::R];
 #pragma unroll
@@ -219,25 +270,19 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     }
 
     for (int64_t p = i0 - 2; p <= i1 + 1; ++p) {
+      ooff += plane;
       mbar_wait(full + 8 * stage, phase);
-      const uint32_t st = smem + stage * C::STAGE_BYTES;
-      double2 c[C::R], up, dn;
+      mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
+      const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
+      double2 c[C::R];
       double km[C::R], kp[C::R];
-      {
-        auto pair_at = [&](int s) -> double2 {
-          const uint32_t ad = own_wl ? st + C::WL_OFF + wrap_row(s)
-                                     : (own_wr ? st + C::WR_OFF + wrap_row(s) : st + main_row(s) + cb);
-          return lds_v2(ad);
-        };
-        up = pair_at(q0);
-        dn = pair_at(q0 + C::R + 1);
+      const double2 up = lds_v2(sb);
+      const double2 dn = lds_v2(sb + (C::R + 1) * P);
 #pragma unroll
-        for (int r = 0; r < C::R; ++r) {
-          const int s = q0 + 1 + r;
-          c[r] = pair_at(s);
-          km[r] = lds_f64(km_wl ? st + C::WL_OFF + wrap_row(s) + 8 : st + main_row(s) + kmb);
-          kp[r] = lds_f64(kp_wr ? st + C::WR_OFF + wrap_row(s) : st + main_row(s) + kpb);
-        }
+      for (int r = 0; r < C::R; ++r) {
+        c[r] = lds_v2(sb + (1 + r) * P);
+        km[r] = lds_f64(sb + (1 + r) * P - 8);
+        kp[r] = lds_f64(sb + (1 + r) * P + 16);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + 8 * stage);
@@ -247,26 +292,25 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
       double2 l1[C::R];
 #pragma unroll
       for (int r = 0; r < C::R; ++r) {
-        l1[r].x = lf_acc(part1[r].x, w6, c[r].x);
-        l1[r].y = lf_acc(part1[r].y, w6, c[r].y);
+        l1[r].x = lf_acc<UNIT>(part1[r].x, w6, c[r].x);
+        l1[r].y = lf_acc<UNIT>(part1[r].y, w6, c[r].y);
       }
       // level 2 of plane p-2: the (+1,0,0) branch is level 1 of plane p-1 -- done, store it
       if (p >= i0 + 2 && store_cols) {
-        double* orow = a.out + ((p - 2) * a.n1 + j) * a.n2 + k;
+        double* orow = a.out + ooff;
 #pragma unroll
         for (int r = 0; r < C::R; ++r) {
-          const int q = q0 + r;
-          if (q >= 1 && q <= C::CJ - 2)
-            st_global_v2(orow + (int64_t)r * a.n2, lf_acc(part2[r].x, w6, l1[r].x),
-                         lf_acc(part2[r].y, w6, l1[r].y));
+          if ((rowmask >> r) & 1u)
+            st_global_v2(orow + (int64_t)r * a.n2, lf_acc<UNIT>(part2[r].x, w6, l1[r].x),
+                         lf_acc<UNIT>(part2[r].y, w6, l1[r].y));
         }
       }
       // hand level 1 of plane p-1 to the neighbours
-      const uint32_t xb = xbuf + xsel * C::X_BYTES;
+      const uint32_t xb = xbuf + xsel * C::X_BYTES + tb;
       xsel ^= 1;
       if (worker) {
 #pragma unroll
-        for (int r = 0; r < C::R; ++r) sts_v2(xb + x_own + r * C::XP, l1[r].x, l1[r].y);
+        for (int r = 0; r < C::R; ++r) sts_v2(xb + (1 + r) * P, l1[r].x, l1[r].y);
       }
       // first six branches of level 1 of plane p (keeps the FP64 pipe busy while warps gather)
 #pragma unroll
@@ -274,36 +318,37 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
         const double2 jm = (r == 0) ? up : c[r - 1];
         const double2 jp = (r == C::R - 1) ? dn : c[r + 1];
         double x = 0.0, y = 0.0;
-        x = lf_acc(x, w0, below0[r].x);  y = lf_acc(y, w0, below0[r].y);
-        x = lf_acc(x, w1, jm.x);         y = lf_acc(y, w1, jm.y);
-        x = lf_acc(x, w2, km[r]);        y = lf_acc(y, w2, c[r].x);
-        x = lf_acc(x, w3, c[r].x);       y = lf_acc(y, w3, c[r].y);
-        x = lf_acc(x, w4, c[r].y);       y = lf_acc(y, w4, kp[r]);
-        x = lf_acc(x, w5, jp.x);         y = lf_acc(y, w5, jp.y);
+        x = lf_acc<UNIT>(x, w0, below0[r].x);  y = lf_acc<UNIT>(y, w0, below0[r].y);
+        x = lf_acc<UNIT>(x, w1, jm.x);         y = lf_acc<UNIT>(y, w1, jm.y);
+        x = lf_acc<UNIT>(x, w2, km[r]);        y = lf_acc<UNIT>(y, w2, c[r].x);
+        x = lf_acc<false>(x, w3, c[r].x);      y = lf_acc<false>(y, w3, c[r].y);
+        x = lf_acc<UNIT>(x, w4, c[r].y);       y = lf_acc<UNIT>(y, w4, kp[r]);
+        x = lf_acc<UNIT>(x, w5, jp.x);         y = lf_acc<UNIT>(y, w5, jp.y);
         part1[r] = make_double2(x, y);
         below0[r] = c[r];
       }
       named_bar_sync(1, C::CONSUMERS);
-      // first six branches of level 2 of plane p-1
+      // first six branches of level 2 of plane p-1 (rows outside the tile read the spare rows of
+      // the exchange tile: whatever is there only reaches level-2 rows that are never stored)
       {
-        const double2 up1 = lds_v2(xb + x_up);
-        const double2 dn1 = lds_v2(xb + x_dn);
+        const double2 up1 = lds_v2(xb);
+        const double2 dn1 = lds_v2(xb + (C::R + 1) * P);
 #pragma unroll
         for (int r = 0; r < C::R; ++r) {
-          km[r] = lds_f64(xb + x_km + r * C::XP);
-          kp[r] = lds_f64(xb + x_kp + r * C::XP);
+          km[r] = lds_f64(xb + (1 + r) * P - 8);
+          kp[r] = lds_f64(xb + (1 + r) * P + 16);
         }
 #pragma unroll
         for (int r = 0; r < C::R; ++r) {
           const double2 jm = (r == 0) ? up1 : l1[r - 1];
           const double2 jp = (r == C::R - 1) ? dn1 : l1[r + 1];
           double x = 0.0, y = 0.0;
-          x = lf_acc(x, w0, below1[r].x);  y = lf_acc(y, w0, below1[r].y);
-          x = lf_acc(x, w1, jm.x);         y = lf_acc(y, w1, jm.y);
-          x = lf_acc(x, w2, km[r]);        y = lf_acc(y, w2, l1[r].x);
-          x = lf_acc(x, w3, l1[r].x);      y = lf_acc(y, w3, l1[r].y);
-          x = lf_acc(x, w4, l1[r].y);      y = lf_acc(y, w4, kp[r]);
-          x = lf_acc(x, w5, jp.x);         y = lf_acc(y, w5, jp.y);
+          x = lf_acc<UNIT>(x, w0, below1[r].x);  y = lf_acc<UNIT>(y, w0, below1[r].y);
+          x = lf_acc<UNIT>(x, w1, jm.x);         y = lf_acc<UNIT>(y, w1, jm.y);
+          x = lf_acc<UNIT>(x, w2, km[r]);        y = lf_acc<UNIT>(y, w2, l1[r].x);
+          x = lf_acc<false>(x, w3, l1[r].x);     y = lf_acc<false>(y, w3, l1[r].y);
+          x = lf_acc<UNIT>(x, w4, l1[r].y);      y = lf_acc<UNIT>(y, w4, kp[r]);
+          x = lf_acc<UNIT>(x, w5, jp.x);         y = lf_acc<UNIT>(y, w5, jp.y);
           part2[r] = make_double2(x, y);
           below1[r] = l1[r];
         }
@@ -315,13 +360,14 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 // ---- configurations ---------------------------------------------------------------------
 typedef void (*LapFusedKernel)(const LapFusedMaps, const LapFusedArgs);
 struct LapFusedConfig {
-  int BJ, BK, CK, threads, smem;
-  LapFusedKernel kernel;
+  int BJ, BK, BKP, threads, smem;
+  LapFusedKernel kernel_unit, kernel_general;  // off-centre weights all exactly 1.0 / any weights
   const char* name;
 };
 template <class C>
 constexpr LapFusedConfig make_lapf(const char* name) {
-  return LapFusedConfig{C::BJ, C::BK, C::CK, C::THREADS, C::SMEM_BYTES, lap7_fused2_kernel<C>, name};
+  return LapFusedConfig{C::BJ, C::BK, C::BKP, C::THREADS, C::SMEM_BYTES, lap7_fused2_kernel<C, true>,
+                        lap7_fused2_kernel<C, false>, name};
 }
 // index 0 is the default; the rest are tuning alternatives (env FDB_LAPF_CFG)
 const LapFusedConfig kLapFused[] = {
@@ -329,12 +375,14 @@ const LapFusedConfig kLapFused[] = {
     make_lapf<LapFusedCfg<16, 3, 3>>("bj16_r3_s3"),
     make_lapf<LapFusedCfg<16, 6, 4>>("bj16_r6_s4"),
     make_lapf<LapFusedCfg<16, 2, 4>>("bj16_r2_s4"),
-    make_lapf<LapFusedCfg<8, 5, 4, 2>>("bj8_r5_s4_2cta"),
+    make_lapf<LapFusedCfg<8, 5, 4, 128, 2>>("bj8_r5_s4_2cta"),
     make_lapf<LapFusedCfg<8, 2, 6>>("bj8_r2_s6"),
     make_lapf<LapFusedCfg<16, 3, 6>>("bj16_r3_s6"),
     make_lapf<LapFusedCfg<16, 6, 6>>("bj16_r6_s6"),
-    make_lapf<LapFusedCfg<8, 5, 8>>("bj8_r5_s8"),
-    make_lapf<LapFusedCfg<16, 3, 8>>("bj16_r3_s8"),
+    make_lapf<LapFusedCfg<16, 3, 4, 64, 2>>("bj16_r3_s4_bk64_2cta"),
+    make_lapf<LapFusedCfg<16, 3, 6, 64, 2>>("bj16_r3_s6_bk64_2cta"),
+    make_lapf<LapFusedCfg<16, 2, 4, 64, 2>>("bj16_r2_s4_bk64_2cta"),
+    make_lapf<LapFusedCfg<8, 5, 6>>("bj8_r5_s6"),
 };
 constexpr int kNumLapFused = sizeof(kLapFused) / sizeof(kLapFused[0]);
 
@@ -356,7 +404,7 @@ const LapFusedConfig* lapf_pick(const Field& f) {
 }
 
 struct LapFusedAttr {
-  const LapFusedConfig* cfg = nullptr;
+  LapFusedKernel fn = nullptr;
   int ctas_per_sm = 1;
   int sms = 148;
 };
@@ -392,7 +440,7 @@ static int lapf_maps(const Field& f, int d, const LapFusedConfig& C, int p, LapF
   const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
   const double* base[3] = {f.body(d, p), f.ghost_lo(d, p), f.ghost_hi(d, p)};
   const int64_t planes[3] = {s.nloc(), f.G, f.G};
-  const int boxes[4][2] = {{C.CK, 2}, {C.CK, C.BJ}, {2, 2}, {2, C.BJ}};
+  const int boxes[4][2] = {{C.BKP, 2}, {C.BKP, C.BJ}, {8, 2}, {8, C.BJ}};
   for (int t = 0; t < 3; ++t)
     for (int b = 0; b < 4; ++b)
       FDB_TRY(encode_tensor_map_3d(&out->m[4 * t + b], base[t], n2, n1, planes[t], boxes[b][0], boxes[b][1]));
@@ -406,17 +454,22 @@ int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend
   const LapFusedConfig* C = lapf_pick(f);
   if (!C) return set_error(FDB_E_INVALID, "no fused 7-point tile divides a %lld x %lld plane",
                            (long long)f.geo.n[1], (long long)f.geo.n[2]);
+  // the Laplacian's six unit weights need no multiply (exact); FDB_LAPF_GENERAL=1 keeps them anyway
+  bool unit = lf_env_int("FDB_LAPF_GENERAL", 0) == 0;
+  for (int i = 0; i < 7; ++i)
+    if (lapf_slot(b.off[i]) != 3 && b.w[i] != 1.0) unit = false;
+  const LapFusedKernel fn = unit ? C->kernel_unit : C->kernel_general;
   LapFusedAttr& at = g_lapf_attr[sl.device & 15];
-  if (at.cfg != C) {
-    FDB_CUDA(cudaFuncSetAttribute(C->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
+  if (at.fn != fn) {
+    FDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
     int nb = 0;
-    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C->kernel, C->threads, C->smem));
+    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, C->threads, C->smem));
     if (nb < 1) return set_error(FDB_E_CUDA, "fused 7-point kernel %s does not fit on an SM", C->name);
     cudaDeviceProp prop;
     FDB_CUDA(cudaGetDeviceProperties(&prop, sl.device));
     at.ctas_per_sm = nb;
     at.sms = prop.multiProcessorCount;
-    at.cfg = C;
+    at.fn = fn;
   }
   if (sl.lapf_cfg != (const void*)C) {
     for (int p = 0; p < 2; ++p) FDB_TRY(lapf_maps(f, d, *C, p, reinterpret_cast<LapFusedMaps*>(sl.lapf_maps[p])));
@@ -446,7 +499,7 @@ int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
   const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
-  C->kernel<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const LapFusedMaps*>(sl.lapf_maps[X]), a);
+  fn<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const LapFusedMaps*>(sl.lapf_maps[X]), a);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;

@@ -24,12 +24,22 @@ def two_applies(x, w):
     ((4, 16, 256), 8, 5, 2),      # 8-row tiles
     ((2, 32, 128), 16, 2, 2),     # thinnest slab
 ])
-def test_model_single_slab(shape, BJ, R, ci):
+@pytest.mark.parametrize("unit", [False, True])
+def test_model_single_slab(shape, BJ, R, ci, unit):
     rng = np.random.default_rng(SEED)
-    x = rng.random(shape)
+    x = rng.random(shape) - 0.5
     w = [1.0, 1.0, 1.0, -6.0, 1.0, 1.0, 1.0]
     out = np.full(shape, np.nan)
-    fused_two_applies(x, w, 0, shape[0], 2, Cfg(BJ, R), ci, 0, shape[0], out)
+    fused_two_applies(x, w, 0, shape[0], 2, Cfg(BJ, R), ci, 0, shape[0], out, unit=unit)
+    assert np.array_equal(out, two_applies(x, w))
+
+
+def test_model_64_cell_tiles():
+    rng = np.random.default_rng(SEED + 2)
+    x = rng.random((4, 16, 192))
+    w = [1.0, 1.0, 1.0, -6.0, 1.0, 1.0, 1.0]
+    out = np.full(x.shape, np.nan)
+    fused_two_applies(x, w, 0, 4, 2, Cfg(16, 3, BK=64), 4, 0, 4, out, unit=True)
     assert np.array_equal(out, two_applies(x, w))
 
 

@@ -241,12 +241,16 @@ def test_fused_two_applies_bitwise(gpu_fb, shape):
         assert np.array_equal(fl.get(), fused)
 
 
-@pytest.mark.parametrize("cfg", range(10))
-def test_fused_two_applies_every_tile_configuration(gpu_fb, cfg, monkeypatch):
+@pytest.mark.parametrize("general", [0, 1])
+@pytest.mark.parametrize("cfg", range(12))
+def test_fused_two_applies_every_tile_configuration(gpu_fb, cfg, general, monkeypatch):
+    """Every tile configuration, with the unit-weight specialisation (the Laplacian's six 1.0 weights are
+    not multiplied) and with the general kernel forced on the same weights."""
     monkeypatch.setenv("FDB_LAPF_CFG", str(cfg))
+    monkeypatch.setenv("FDB_LAPF_GENERAL", str(general))
     monkeypatch.setenv("FDB_TMA_CI", "3")  # ragged chunks of planes
     rng = np.random.default_rng(SEED + 21)
-    a = rng.random((7, 32, 256))
+    a = rng.random((7, 32, 256)) - 0.5
     off, w = oracle.laplacian_stencil(3)
     with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
         assert fl.fuse() == 2

@@ -11,7 +11,7 @@ import fidibench_b200 as fb  # noqa: E402
 import oracle  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-cfgs = [int(x) for x in sys.argv[2:]] or list(range(10))
+cfgs = [int(x) for x in sys.argv[2:]] or list(range(12))
 cis = [int(x) for x in os.environ.get("SWEEP_CIS", "0,64").split(",")]
 ITER = 10
 off, w = oracle.laplacian_stencil(3)
@@ -35,6 +35,9 @@ with fb.Filter([N] * 3, [0.0] * 3, [1.0] * 3, st) as fl:
     fl.set_fuse(1)
     run("fuse=1")
     fl.set_fuse(2)
+    os.environ["FDB_LAPF_GENERAL"] = "1"   # the six unit weights multiplied anyway
+    run("fuse=2 cfg=0 general-weights kernel")
+    os.environ["FDB_LAPF_GENERAL"] = "0"
     for c in cfgs:
         os.environ["FDB_LAPF_CFG"] = str(c)
         for ci in cis:
