@@ -10,7 +10,8 @@ One bench "step" = one Upwind::advect(numTimeSteps=T) call (T = 100, BASELINE
 config 2) over the resident field.  N = 1 runs 512^3 (configs[1]); N > 1 keeps
 512^3 cells per GPU (weak scaling), slabs along axis 0 with an NCCL halo ring:
 N=2 -> 1024x512x512, N=4 -> 1024x1024x512, N=8 -> 1024^3 (configs[2]).
-`--workload upwind1024` runs 1024^3 on every N instead (strong scaling).
+`--workload upwind1024` runs 1024^3 on every N instead (strong scaling);
+`--workload lap1024` is BASELINE configs[3], the 7-point Laplacian iterate loop on 1024^3.
 
 Prints ONE JSON line on rank 0 (see the keys at the bottom of main()).
 """
@@ -44,6 +45,10 @@ def workload_dims(workload: str, n: int):
         return (128, 128, 128), "strong"
     if workload == "upwind2048":     # configs[4], 8 GPUs
         return (2048, 2048, 2048), "strong"
+    if workload == "lap1024":        # configs[3]: 7-point Laplacian, 1024^3, 1 and 8 GPUs
+        return (1024, 1024, 1024), "strong"
+    if workload == "lap512":
+        return (512, 512, 512), "strong"
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -192,6 +197,192 @@ def cpu_baseline(sdims, tsteps_hint=10):
                       f"{'untouched upwind.cxx -O3 -fopenmp' if kind == 'reference' else 'oracle/fdb_oracle.c'}"}
 
 
+def lap_cpu_baseline(niter_hint=2):
+    """The reference's Filter path (cxx/Filter.cpp, untouched, single rank against the MPI stub of
+    oracle/fakempi) on a bounded sample; else the oracle port."""
+    import numpy as np
+    import oracle
+    sdims = (128, 128, 128)
+    off, w = oracle.laplacian_stencil(3)
+    x = oracle.c.laplacian_input(sdims)
+    if oracle.ref_available():
+        kind, cores = "reference", 1
+        run = lambda n: oracle.ref().filter_run(sdims, off, w, init=x, niter=n, want_field=False)["seconds"]
+    else:
+        kind, cores = "port", 1
+        def run(n):
+            t0 = time.perf_counter(); y = x
+            for _ in range(n):
+                y = oracle.c.stencil_apply(y, off, w)
+            return time.perf_counter() - t0
+    t1 = run(1)
+    niter = int(max(1, min(niter_hint, 12.0 / max(t1, 1e-3))))
+    secs = run(niter)
+    return {"value": float(np.prod(sdims)) * niter / secs / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
+            "sample": f"128x128x128 x {niter} x (applyFilter; copyOutToIn), "
+                      f"{'untouched Filter.cpp, 1 rank (MPI stub)' if kind == 'reference' else 'oracle/fdb_oracle.c'}"}
+
+
+def laplacian_reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    dims, scaling = workload_dims(args.workload, args.gpus)
+    cpu, vals = None, []
+    for i in range(args.warmup + args.steps):
+        cpu = lap_cpu_baseline(niter_hint=1)   # one bounded sample per bench step
+        if i >= args.warmup:
+            vals.append(cpu["value"])
+    value = len(vals) / sum(1.0 / v for v in vals)   # total cell-applies / total seconds
+    cpu["value"] = value
+    line = {"impl": "reference", "metric": "GCUPS (FP64 cell-applies/s), laplacian 3-D 7-point", "value": value,
+            "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 128.0 ** 3 / value / 1e6, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"laplacian7 {dims[0]}x{dims[1]}x{dims[2]} (reference arm: bounded sample {cpu['sample']})",
+                       "parallelism": "1 rank"},
+            "cpu_baseline": cpu, "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main_laplacian(args, rank, world, local_rank):
+    """BASELINE configs[3]: the 3-D 7-point Laplacian of laplacian/cxx/laplacian.cxx on 1024^3.  One bench
+    step = the driver's loop, ITER x (applyFilter; copyOutToIn) (ITER = 10, laplacian.cxx:86-90)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fidibench_b200 as fb
+    import oracle
+
+    if not torch.cuda.is_available() or fb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = fb.Comm.from_torch_distributed(device=local_rank)
+    dims, scaling = workload_dims(args.workload, world)
+    ITER = 10
+    off, w = oracle.laplacian_stencil(3)
+    st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
+    fl = fb.Filter(dims, [0.0] * 3, [1.0] * 3, st, comm=comm)
+    if args.kernel == "generic":
+        fl.set_kernel(fb.FDB_KERNEL_GENERIC)
+    if args.fuse:
+        fl.set_fuse(args.fuse)
+    fuse = fl.fuse()
+    tiled = fl.kernel() == fb.FDB_KERNEL_TMA
+    kernel_name = "stencil_generic_kernel" if not tiled else ("lap7_fused2_kernel" if fuse == 2 else "lap7_tma_kernel")
+    nloc = fl.hi - fl.lo
+    slab_cells = nloc * dims[1] * dims[2]
+    total_cells = float(np.prod(dims))
+    # the driver's input function on this rank's planes (ref: laplacian.cxx:22-28, Filter.cpp:103-112),
+    # evaluated on the host as the reference does, in pinned memory
+    x1 = np.sin(2.0 * np.pi * ((np.arange(dims[0]) + 0.5) * (1.0 / float(dims[0]))))
+    host = torch.empty(slab_cells, dtype=torch.float64, pin_memory=True)
+    host_np = host.numpy().reshape(nloc, dims[1], dims[2])
+    np.multiply(x1[fl.lo:fl.hi, None, None] * x1[None, :dims[1], None], x1[None, None, :dims[2]], out=host_np)
+    fl.set_input_slab(host_np)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    if sampler:
+        sampler.mark()
+    for _ in range(args.warmup):
+        fl.iterate(ITER)
+    barrier()
+    launches, ms = 0, 0.0
+    for _ in range(args.steps):
+        # every step starts from the driver's input again (untimed upload): iterating the Laplacian on and on
+        # amplifies roundoff by up to 12x per apply (SURVEY.md H1) and would overflow after ~280 applies
+        fl.set_input_slab(host_np)
+        barrier()
+        l0 = fb.launch_count()
+        fl.iterate(ITER)                       # synchronous; CUDA events on the kernels' stream inside the library
+        launches += fb.launch_count() - l0
+        ms += fl.last_timing()["gpu_ms"]
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    halo = fl.last_timing()["halo_bytes"]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = total_cells * ITER * args.steps / (ms / 1e3) / 1e9
+
+    # end to end with HOST buffers: upload the input, iterate, read the checksums back
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(2, min(args.steps, 3))
+        fl.set_input_slab(host_np); fl.iterate(ITER); fl.computeCheckSum("output")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fl.set_input_slab(host_np)
+            fl.iterate(ITER)
+            chk = fl.computeCheckSum("output")
+        torch.cuda.synchronize()
+        t1 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t1], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t1 = float(t.item())
+        e2e = {"value": total_cells * ITER * e2e_steps / t1 / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": int(slab_cells * 8), "d2h_bytes_per_step": int(dims[0] * 8), "steps": e2e_steps,
+               "checksum": chk, "ms_per_step": t1 / e2e_steps * 1e3,
+               "what": "per step: fdb_stencil_set_input_slab(pinned host) + fdb_stencil_iterate(10) + fdb_stencil_checksum "
+                       "(PCIe-bound: the upload of the input field is most of the step)"}
+
+    peak, peak_src = measured_peak()
+    per_launch = 2 if fuse == 2 else 1
+    n_kernel_launches = (ITER // per_launch + ITER % per_launch) * args.steps
+    avg_launch_ms = ms / n_kernel_launches
+    algo_bytes_per_launch = slab_cells * ALGO_BYTES_PER_UPDATE * ITER * args.steps / n_kernel_launches
+    achieved = algo_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(f"{kernel_name}:{nloc}x{dims[1]}x{dims[2]}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+                "applies_per_launch": per_launch,
+                "dram_frac": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "how": "16 B per cell-apply x cell-applies of one launch / (CUDA-event time / launches); the fused kernel "
+                       "does two applies per launch, so the algorithmic figure may exceed the copy roofline -- "
+                       "`traffic`/`dram_frac` are the measured DRAM bytes"}
+    cpu = lap_cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if rank == 0:
+        line = {"metric": "GCUPS (FP64 cell-applies/s), laplacian 3-D 7-point", "value": value, "unit": "GCUPS",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (the driver's prod sin(2 pi x) input, evaluated on the host)",
+                "config": {"workload": f"laplacian7 {dims[0]}x{dims[1]}x{dims[2]}, {ITER} x (apply; copyOutToIn) per step",
+                           "cells_per_gpu": int(slab_cells), "parallelism": f"slab{world}" if world > 1 else "single",
+                           "kernel": kernel_name, "applies_per_sweep": per_launch,
+                           "l2": "inputs larger than L2 (2 ping-pong fields of %.2f GiB per GPU)" % (slab_cells * 8 / 2**30)},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "halo_bytes_per_gpu": halo}
+        print(json.dumps(line), flush=True)
+    fl.close()
+    if comm is not None:
+        comm.close()
+        dist.destroy_process_group()
+    return 0
+
+
 # --------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -210,9 +401,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        return reference_arm(args, rank, world)
+        return laplacian_reference_arm(args, rank) if args.workload.startswith("lap") else reference_arm(args, rank, world)
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.workload.startswith("lap"):
+        if world != args.gpus:
+            raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch N>1 with torch.distributed.run")
+        return main_laplacian(args, rank, world, local_rank)
 
     import numpy as np
     import torch

@@ -369,7 +369,9 @@ constexpr LapFusedConfig make_lapf(const char* name) {
   return LapFusedConfig{C::BJ, C::BK, C::BKP, C::THREADS, C::SMEM_BYTES, lap7_fused2_kernel<C, true>,
                         lap7_fused2_kernel<C, false>, name};
 }
-// index 0 is the default; the rest are tuning alternatives (env FDB_LAPF_CFG)
+// kDefaultLapFused is the default (round-1 sweeps on a B200, profiles/r01j_*: six rows per thread,
+// 7 consumer warps, 242 registers -- 639 GCUPS at 1024^3, 611 at 512^3); the rest are tuning
+// alternatives (env FDB_LAPF_CFG)
 const LapFusedConfig kLapFused[] = {
     make_lapf<LapFusedCfg<16, 3, 4>>("bj16_r3_s4"),
     make_lapf<LapFusedCfg<16, 3, 3>>("bj16_r3_s3"),
@@ -385,6 +387,7 @@ const LapFusedConfig kLapFused[] = {
     make_lapf<LapFusedCfg<8, 5, 6>>("bj8_r5_s6"),
 };
 constexpr int kNumLapFused = sizeof(kLapFused) / sizeof(kLapFused[0]);
+constexpr int kDefaultLapFused = 7;  // bj16_r6_s6
 
 int lf_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -394,8 +397,8 @@ int lf_env_int(const char* name, int dflt) {
 // the first configuration (from the forced or default one on) whose tile divides the plane
 const LapFusedConfig* lapf_pick(const Field& f) {
   const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
-  int first = lf_env_int("FDB_LAPF_CFG", 0);
-  if (first < 0 || first >= kNumLapFused) first = 0;
+  int first = lf_env_int("FDB_LAPF_CFG", kDefaultLapFused);
+  if (first < 0 || first >= kNumLapFused) first = kDefaultLapFused;
   for (int t = 0; t < kNumLapFused; ++t) {
     const LapFusedConfig& C = kLapFused[(first + t) % kNumLapFused];
     if (n1 % C.BJ == 0 && n2 % C.BK == 0) return &C;
@@ -491,9 +494,17 @@ int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend
   const int64_t planes = iend - ibeg;
   int64_t ci = lf_env_int("FDB_TMA_CI", 0);
   if (ci <= 0) {
-    // every work item warms up on four extra planes: favour long chunks
-    ci = 128;
-    while (ci > 8 && tiles * ((planes + ci - 1) / ci) < 2 * grid_max) ci /= 2;
+    // Static round-robin: the sweep takes ceil(items / CTAs) rounds of (chunk + 4 warm-up planes)
+    // plane-steps.  Long chunks amortise the warm-up, short ones fill the last round: take the
+    // cheapest of a few lengths (measured: 64 beats 128 at 512^3, 128 beats 64 at 1024^3).
+    static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 24, 16, 8};
+    int64_t best_cost = -1;
+    for (int c : cand) {
+      const int64_t cc = c < planes ? c : planes;
+      const int64_t items = tiles * ((planes + cc - 1) / cc);
+      const int64_t cost = ((items + grid_max - 1) / grid_max) * (cc + 4);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; ci = cc; }
+    }
   }
   if (ci > planes) ci = planes;
   a.ci = (int)ci;

@@ -86,9 +86,17 @@ int encode_tensor_map_3d(CUtensorMap* tm, const double* base, int64_t n2, int64_
   cuuint64_t strides[2] = {(cuuint64_t)n2 * 8, (cuuint64_t)n2 * (cuuint64_t)n1 * 8};
   cuuint32_t box[3] = {(cuuint32_t)box2, (cuuint32_t)box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  // L2 promotion of the TMA requests: 256 B unless FDB_TMA_L2PROMO says 0 (none), 64 or 128 (tuning)
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* pv = getenv("FDB_TMA_L2PROMO")) {
+    const int v = atoi(pv);
+    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                   : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                              : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+  }
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(FDB_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) dims=%lldx%lldx%lld box=%dx%d",
                      (int)r, (long long)n0, (long long)n1, (long long)n2, box1, box2);

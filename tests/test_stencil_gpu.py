@@ -280,7 +280,7 @@ def test_fused_laplacian_driver_sequence_128(gpu_fb):
 def test_fuse_falls_back_and_validates(gpu_fb):
     off, w = oracle.laplacian_stencil(3)
     # a plane the fused tile does not divide: auto = 1, asking for 2 is an error
-    with gpu_fb.Filter((8, 16, 64), [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
+    with gpu_fb.Filter((8, 16, 96), [0.0] * 3, [1.0] * 3, as_dict(off, w)) as fl:
         assert fl.fuse() == 1
         with pytest.raises(gpu_fb.FdbError):
             fl.set_fuse(2)
