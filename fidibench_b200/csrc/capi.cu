@@ -33,11 +33,21 @@ struct fdb_stencil {
 
 namespace {
 
+constexpr int kDefaultFusedImpl = 1;  // which fused kernel runs (FDB_FUSED_IMPL overrides): kernels_fused.cu / _fused2.cu
+
+int fused_impl() {
+  const char* v = getenv("FDB_FUSED_IMPL");
+  const int i = (v && *v) ? atoi(v) : kDefaultFusedImpl;
+  return i == 2 ? 2 : 1;
+}
+
 struct UpwindSweep : SweepLauncher {
   UpwindCoeffs k;
   bool tma = false;
+  int impl = 1;
   // depth = time steps this sweep advances (> 1: the fused temporal-blocking kernel)
   int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) override {
+    if (depth > 1 && impl == 2) return launch_upwind_fused2(*f, d, X, depth, ibeg, iend, k, s);
     if (depth > 1) return launch_upwind_fused(*f, d, X, depth, ibeg, iend, k, s);
     return tma ? launch_upwind_tma(*f, d, X, ibeg, iend, k, s)
                : launch_upwind_generic(*f, d, X, ibeg, iend, k, s);
@@ -47,6 +57,7 @@ struct UpwindSweep : SweepLauncher {
   int launch_push(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s, double* peer_out,
                   int64_t peer_from) override {
     if (!tma) return FDB_E_STATE;
+    if (depth > 1 && impl == 2) return launch_upwind_fused2(*f, d, X, depth, ibeg, iend, k, s, peer_out, peer_from);
     if (depth > 1) return launch_upwind_fused(*f, d, X, depth, ibeg, iend, k, s, peer_out, peer_from);
     return launch_upwind_tma(*f, d, X, ibeg, iend, k, s, peer_out, peer_from);
   }
@@ -485,6 +496,7 @@ int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTim
   int kern = FDB_KERNEL_GENERIC;
   FDB_TRY(fdb_upwind_get_kernel(h, &kern));
   sw.tma = (kern == FDB_KERNEL_TMA);
+  sw.impl = fused_impl();
   const int want = (h->fuse == 0) ? kAutoFuse : h->fuse;
   const int fuse = (sw.tma && want > 1 && upwind_fused_supported(*f, sw.k, want)) ? want : 1;
   // plan: sweeps of `fuse` time steps, then the remainder

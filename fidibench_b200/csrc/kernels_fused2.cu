@@ -1,0 +1,460 @@
+// kernels_fused2.cu -- temporal blocking for the 3-D upwind step, second layout.
+//
+// Same algorithm as kernels_fused.cu (T time steps per sweep, one-sided halos, plane i-1 of every
+// level carried in registers, levels >= 1 exchanged through two ping-pong shared-memory tiles,
+// bit-identical to T single steps) with the shared-memory layout of kernels_lapfused.cu:
+//
+//   * ONE row pitch for the whole stage.  Rows are BKP = BK + 8 cells wide (global columns
+//     k0-8 .. k0+BK-1) so that two rows are a multiple of 128 bytes; the halo box holds HR rows
+//     (T rounded up to even) and the tile rows follow it directly.  Every shared-memory access of a
+//     consumer thread is `base + immediate`: no per-row selects, no per-plane address arithmetic.
+//   * the periodic wrap columns of the first k-tile (an 8-cell box at column N2-8) are copied into
+//     the zero-filled cells of the tile rows by the LOADER warp, which issues the TMA boxes and,
+//     a few planes later, hands each stage to the consumers; the consumers never see the wrap.
+//   * the exchange tiles use the same pitch and column offsets, with a spare row on top, so the
+//     stage and the exchange tile are addressed from the same thread base.
+//   * output addresses advance by one plane per iteration instead of being rebuilt.
+#include "fdb_internal.h"
+#include "tma_ptx.cuh"
+
+namespace fdb {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int f2_align128(int x) { return (x + 127) / 128 * 128; }
+
+template <int T_, int CJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1>
+struct Fused2Cfg {
+  static constexpr int T = T_, CJ = CJ_, R = R_, STAGES = STAGES_, BK = BK_, MINB = MINB_;
+  static constexpr int HKC = 2 * (T / 2);          // redundant compute columns on the left (even, >= T-1)
+  static constexpr int CK = BK + HKC;              // compute columns: global k0-HKC .. k0+BK-1
+  static constexpr int TX = CK / 2;                // threads per row (2 cells each)
+  static constexpr int TY = CJ / R;
+  static constexpr int WORKERS = TX * TY;
+  static constexpr int CONSUMERS = (WORKERS + 31) / 32 * 32;
+  static constexpr int CONSUMER_WARPS = CONSUMERS / 32;
+  static constexpr int THREADS = CONSUMERS + 32;   // + the loader warp
+  static constexpr int BJ = CJ - (T - 1);          // output rows per tile: global j0 .. j0+BJ-1
+  static constexpr int HR = (T + 1) / 2 * 2;       // halo rows loaded above the tile: global j0-HR .. j0-1
+  static constexpr int IN_ROWS = HR + BJ;          // stage rows; compute row q is stage row q + HR - T + 1
+  static constexpr int BKP = BK + 8;               // stage columns: global k0-8 .. k0+BK-1
+  static constexpr int LEFT = 8 - HKC;             // stage column of the first compute column
+  static constexpr int PITCH = BKP * 8;
+  static constexpr int BODY_OFF = HR * PITCH;
+  static constexpr int MAIN_BYTES = IN_ROWS * PITCH;
+  static constexpr int WPITCH = 64;                // wrap box rows: 8 cells, global columns N2-8 .. N2-1
+  static constexpr int W_OFF = f2_align128(MAIN_BYTES);
+  static constexpr int STAGE_BYTES = f2_align128(W_OFF + IN_ROWS * WPITCH);
+  static constexpr int TX_MAIN = IN_ROWS * PITCH;
+  static constexpr int TX_WRAP = IN_ROWS * WPITCH;
+  static constexpr int X_BYTES = f2_align128((CJ + 1) * PITCH);  // exchange tile: compute row q at row q + 1
+  static constexpr int NX = (T > 1) ? 2 : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NX * X_BYTES + 3 * STAGES * 8 + 128;
+  static constexpr int LAG = STAGES - 2;
+  static_assert(CJ % R == 0 && T >= 2 && T <= 4 && HKC >= T - 1 && CJ > T, "bad fused tile");
+  static_assert((HR * PITCH) % 128 == 0 && (HR * WPITCH) % 128 == 0, "misaligned TMA destination");
+  static_assert(BKP <= 256 && BJ <= 256, "TMA box limit");
+  static_assert(IN_ROWS <= 32, "one loader lane per stage row");
+  static_assert(STAGES >= 3, "the loader needs two stages of slack");
+  static_assert(THREADS <= 1024, "too many threads");
+};
+
+struct Fused2Args {
+  double* out;
+  int64_t n1, n2;
+  int64_t ibeg, iend;
+  int ci, njt, nkt;
+  int64_t nwork;
+  int G;  // planes in the ghost tensor; local plane p < 0 is its plane G + p
+  double c0, c1, c2;
+  double* peer_out;   // planes p >= peer_from are also stored here (the next slab's ghost planes), or null
+  int64_t peer_from;
+};
+
+// Tensor maps: m[0..3] over the local planes, m[4..7] over the ghost planes below; box shapes
+//   0/4: {BKP, HR} halo rows   1/5: {BKP, BJ} tile rows   2/6: {8, HR} wrap corner   3/7: {8, BJ} wrap columns
+struct Fused2Maps {
+  CUtensorMap m[8];
+};
+
+// one upwind update of a cell (ref: upwind.cxx:72-80)
+__device__ __forceinline__ double upwind_cell2(double ctr, double im1, double jm1, double km1, double c0,
+                                               double c1, double c2) {
+  double t = ctr;
+  t = __dsub_rn(t, __dmul_rn(c0, __dsub_rn(im1, ctr)));
+  t = __dsub_rn(t, __dmul_rn(c1, __dsub_rn(jm1, ctr)));
+  t = __dsub_rn(t, __dmul_rn(c2, __dsub_rn(km1, ctr)));
+  return t;
+}
+
+// position of the loader in the sequence of (work item, plane) pairs of this CTA
+template <class C>
+struct Fused2Cursor {
+  int64_t w, p, i1;
+  int kt, jt;
+  __device__ __forceinline__ void open(const Fused2Args& a) {
+    kt = (int)(w % a.nkt);
+    jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    p = i0 - C::T;
+  }
+  __device__ __forceinline__ bool valid(const Fused2Args& a) const { return w < a.nwork; }
+  __device__ __forceinline__ void next(const Fused2Args& a) {
+    if (++p >= i1) {
+      w += gridDim.x;
+      if (w < a.nwork) open(a);
+    }
+  }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+    upwind3d_fused2_kernel(const __grid_constant__ Fused2Maps maps, const Fused2Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
+  const uint32_t landed = xbuf + C::NX * C::X_BYTES;  // TMA bytes of the stage have arrived
+  const uint32_t full = landed + C::STAGES * 8;        // ... and its wrap columns are in place
+  const uint32_t empty = full + C::STAGES * 8;         // every consumer warp has read the stage
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    // ===================== loader warp (see kernels_lapfused.cu) =====================
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) prefetch_tmap(&maps.m[m]);
+    }
+    Fused2Cursor<C> ci, cf;  // issue / hand-over
+    ci.w = blockIdx.x;
+    if (ci.valid(a)) ci.open(a);
+    cf = ci;
+    int si = 0, sf = 0;
+    uint32_t phi = 0, phf = 0;
+    int ahead = 0;
+    while (cf.valid(a)) {
+      if (ci.valid(a)) {
+        mbar_wait(empty + 8 * si, phi ^ 1);
+        if (lane == 0) {
+          const uint32_t st = smem + si * C::STAGE_BYTES;
+          const uint32_t lb = landed + 8 * si;
+          const int kb = ci.kt * C::BK - 8;  // first stage column (negative for the first k-tile: zero fill)
+          const int j0 = ci.jt * C::BJ;
+          const int jh = (j0 - C::HR < 0) ? j0 - C::HR + (int)a.n1 : j0 - C::HR;  // periodic halo rows
+          const bool first_k = (ci.kt == 0);
+          const int64_t p = ci.p;
+          const int g = (p < 0) ? 4 : 0;  // ghost tensor below the slab
+          const int pl = (p < 0) ? a.G + (int)p : (int)p;
+          mbar_expect_tx(lb, C::TX_MAIN + (first_k ? C::TX_WRAP : 0));
+          tma_load_3d(st, &maps.m[g + 0], lb, kb, jh, pl);
+          tma_load_3d(st + C::BODY_OFF, &maps.m[g + 1], lb, kb, j0, pl);
+          if (first_k) {
+            tma_load_3d(st + C::W_OFF, &maps.m[g + 2], lb, (int)a.n2 - 8, jh, pl);
+            tma_load_3d(st + C::W_OFF + C::HR * C::WPITCH, &maps.m[g + 3], lb, (int)a.n2 - 8, j0, pl);
+          }
+        }
+        ci.next(a);
+        if (++si == C::STAGES) { si = 0; phi ^= 1; }
+        ++ahead;
+      }
+      if (ahead > C::LAG || !ci.valid(a)) {
+        mbar_wait(landed + 8 * sf, phf);
+        if (cf.kt == 0 && lane < C::IN_ROWS) {
+          // columns -6 .. -1 of the tile rows <- columns N2-6 .. N2-1 (a sweep of T <= 4 steps reads
+          // back to column -(HKC + 1) >= -5)
+          const uint32_t st = smem + sf * C::STAGE_BYTES;
+          const double2 v0 = lds_v2(st + C::W_OFF + lane * C::WPITCH + 16);
+          const double2 v1 = lds_v2(st + C::W_OFF + lane * C::WPITCH + 32);
+          const double2 v2 = lds_v2(st + C::W_OFF + lane * C::WPITCH + 48);
+          sts_v2(st + lane * C::PITCH + 16, v0.x, v0.y);
+          sts_v2(st + lane * C::PITCH + 32, v1.x, v1.y);
+          sts_v2(st + lane * C::PITCH + 48, v2.x, v2.y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * sf);
+        cf.next(a);
+        if (++sf == C::STAGES) { sf = 0; phf ^= 1; }
+        --ahead;
+      }
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  const bool worker = tid < C::WORKERS;  // threads past the tile only keep the barriers company
+  const int wid = worker ? tid : 0;
+  const int tx = wid % C::TX;
+  const int ty = wid / C::TX;
+  const int q0 = ty * C::R;  // first compute row of this thread (compute row q = global row j0-(T-1)+q)
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t xsel = 0;
+  const double c0 = a.c0, c1 = a.c1, c2 = a.c2;
+  constexpr uint32_t P = C::PITCH;
+  // thread base: the row above the thread's first row, its own pair.  Exchange tile: compute row q
+  // at tile row q + 1; stage: compute row q at stage row q + HR - T + 1.
+  const uint32_t xt = q0 * P + (C::LEFT + 2 * tx) * 8;
+  const uint32_t tb = xt + (C::HR - C::T) * P;
+  // rows of this thread that belong to the output tile (compute rows T-1 .. CJ-1)
+  uint32_t rowmask = 0;
+#pragma unroll
+  for (int r = 0; r < C::R; ++r)
+    if (q0 + r >= C::T - 1) rowmask |= 1u << r;
+  const int64_t plane = a.n1 * a.n2;
+
+  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    const int kt = (int)(w % a.nkt);
+    const int jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;   // global column of this thread's first cell
+    const int64_t j = (int64_t)jt * C::BJ - (C::T - 1) + q0;   // global row of this thread's first row
+    const bool store_cols = worker && (2 * tx >= C::HKC) && (k < a.n2);
+    // rows of the output tile that exist (the last j-tile may be ragged)
+    uint32_t rmask = rowmask;
+#pragma unroll
+    for (int r = 0; r < C::R; ++r)
+      if (j + r >= a.n1) rmask &= ~(1u << r);
+    // offset of (plane p, row j, column k), advanced by one plane per iteration
+    int64_t ooff = ((i0 - C::T - 1) * a.n1 + j) * a.n2 + k;
+
+    double2 carry[C::T][C::R];  // plane i-1 of levels 0..T-1
+#pragma unroll
+    for (int s = 0; s < C::T; ++s)
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) carry[s][r] = make_double2(0.0, 0.0);
+
+    for (int64_t p = i0 - C::T; p < i1; ++p) {
+      ooff += plane;
+      mbar_wait(full + 8 * stage, phase);
+      mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
+      const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
+      double2 v[C::R];
+      double km[C::R];
+      double2 up = lds_v2(sb);
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        v[r] = lds_v2(sb + (1 + r) * P);
+        km[r] = lds_f64(sb + (1 + r) * P - 8);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+
+#pragma unroll
+      for (int s = 0; s < C::T; ++s) {
+        double2 nv[C::R];
+#pragma unroll
+        for (int r = 0; r < C::R; ++r) {
+          const double2 jm = (r == 0) ? up : v[r - 1];
+          nv[r].x = upwind_cell2(v[r].x, carry[s][r].x, jm.x, km[r], c0, c1, c2);
+          nv[r].y = upwind_cell2(v[r].y, carry[s][r].y, jm.y, v[r].x, c0, c1, c2);
+          carry[s][r] = v[r];
+        }
+        if (s == C::T - 1) {
+          if (p >= i0 && store_cols) {
+            double* orow = a.out + ooff;
+            const bool push = (a.peer_out != nullptr) && (p >= a.peer_from);
+            double* prow = a.peer_out + (ooff - a.peer_from * plane);
+#pragma unroll
+            for (int r = 0; r < C::R; ++r) {
+              if ((rmask >> r) & 1u) {
+                st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+                if (push) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+              }
+            }
+          }
+        } else {
+          // hand level s+1 of this plane to the neighbours through the exchange tile
+          const uint32_t xb = xbuf + xsel * C::X_BYTES + xt;
+          xsel ^= 1;
+          if (worker) {
+#pragma unroll
+            for (int r = 0; r < C::R; ++r) sts_v2(xb + (1 + r) * P, nv[r].x, nv[r].y);
+          }
+          named_bar_sync(1, C::CONSUMERS);
+          up = lds_v2(xb);
+#pragma unroll
+          for (int r = 0; r < C::R; ++r) {
+            km[r] = lds_f64(xb + (1 + r) * P - 8);
+            v[r] = nv[r];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- configurations ---------------------------------------------------------------------
+typedef void (*Fused2Kernel)(const Fused2Maps, const Fused2Args);
+struct Fused2Config {
+  int T, CJ, BJ, BK, BKP, HR, threads, smem;
+  Fused2Kernel kernel;
+  const char* name;
+};
+template <class C>
+constexpr Fused2Config make_fused2(const char* name) {
+  return Fused2Config{C::T, C::CJ, C::BJ, C::BK, C::BKP, C::HR, C::THREADS, C::SMEM_BYTES,
+                      upwind3d_fused2_kernel<C>, name};
+}
+// per T: index 0 is the default, the rest are tuning alternatives (env FDB_FUSED_CFG)
+const Fused2Config kF2_2[] = {
+    make_fused2<Fused2Cfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),
+    make_fused2<Fused2Cfg<2, 18, 6, 4>>("t2_cj18_r6_s4"),
+    make_fused2<Fused2Cfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),
+    make_fused2<Fused2Cfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),
+};
+const Fused2Config kF2_3[] = {
+    make_fused2<Fused2Cfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),
+    make_fused2<Fused2Cfg<3, 18, 6, 4>>("t3_cj18_r6_s4"),
+    make_fused2<Fused2Cfg<3, 18, 6, 6>>("t3_cj18_r6_s6"),
+    make_fused2<Fused2Cfg<3, 21, 7, 6>>("t3_cj21_r7_s6"),
+    make_fused2<Fused2Cfg<3, 18, 3, 4, 64, 2>>("t3_cj18_r3_s4_bk64_2cta"),
+    make_fused2<Fused2Cfg<3, 21, 3, 6>>("t3_cj21_r3_s6"),
+    make_fused2<Fused2Cfg<3, 20, 5, 6>>("t3_cj20_r5_s6"),
+    make_fused2<Fused2Cfg<3, 24, 8, 6>>("t3_cj24_r8_s6"),
+};
+const Fused2Config kF2_4[] = {
+    make_fused2<Fused2Cfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
+    make_fused2<Fused2Cfg<4, 24, 8, 6>>("t4_cj24_r8_s6"),
+    make_fused2<Fused2Cfg<4, 18, 6, 6>>("t4_cj18_r6_s6"),
+    make_fused2<Fused2Cfg<4, 20, 4, 6>>("t4_cj20_r4_s6"),
+};
+
+const Fused2Config* f2_table(int T, int* count) {
+  switch (T) {
+    case 2: *count = sizeof(kF2_2) / sizeof(kF2_2[0]); return kF2_2;
+    case 3: *count = sizeof(kF2_3) / sizeof(kF2_3[0]); return kF2_3;
+    case 4: *count = sizeof(kF2_4) / sizeof(kF2_4[0]); return kF2_4;
+  }
+  *count = 0;
+  return nullptr;
+}
+
+int f2_env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+const Fused2Config* f2_pick(int T) {
+  int n = 0;
+  const Fused2Config* tab = f2_table(T, &n);
+  if (!tab) return nullptr;
+  int c = f2_env_int("FDB_FUSED_CFG", 0);
+  if (c < 0 || c >= n) c = 0;
+  return &tab[c];
+}
+
+struct Fused2Attr {
+  const Fused2Config* cfg = nullptr;
+  int ctas_per_sm = 1;
+  int sms = 148;
+};
+Fused2Attr g_f2_attr[16][kMaxFuse + 1];
+
+int f2_maps(const Field& f, int d, const Fused2Config& C, int p, Fused2Maps* out) {
+  const Slab& s = f.slabs[d];
+  const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
+  const double* base[2] = {f.body(d, p), f.ghost_lo(d, p)};
+  const int64_t planes[2] = {s.nloc(), f.G};
+  const int boxes[4][2] = {{C.BKP, C.HR}, {C.BKP, C.BJ}, {8, C.HR}, {8, C.BJ}};
+  for (int t = 0; t < 2; ++t)
+    for (int b = 0; b < 4; ++b)
+      FDB_TRY(encode_tensor_map_3d(&out->m[4 * t + b], base[t], n2, n1, planes[t], boxes[b][0], boxes[b][1]));
+  return FDB_OK;
+}
+
+}  // namespace
+
+// what the second layout adds to upwind_fused_supported(): the halo box is HR = 4 rows for T = 3
+bool upwind_fused2_supported(const Field& f, int T) {
+  return f.geo.n[1] >= 8 && f.geo.n[2] >= 16 && f2_pick(T) != nullptr;
+}
+
+const char* upwind_fused2_name(int T) {
+  const Fused2Config* C = f2_pick(T);
+  return C ? C->name : "";
+}
+
+int launch_upwind_fused2(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                         cudaStream_t s, double* peer_out, int64_t peer_from) {
+  if (iend <= ibeg) return FDB_OK;
+  Slab& sl = f.slabs[d];
+  Fused2Attr& at = g_f2_attr[sl.device & 15][T];
+  const Fused2Config* C = f2_pick(T);
+  if (!C) return set_error(FDB_E_INVALID, "no fused kernel for %d steps per sweep", T);
+  if (at.cfg != C) {
+    FDB_CUDA(cudaFuncSetAttribute(C->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
+    int nb = 0;
+    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C->kernel, C->threads, C->smem));
+    if (nb < 1) return set_error(FDB_E_CUDA, "fused kernel %s does not fit on an SM", C->name);
+    cudaDeviceProp prop;
+    FDB_CUDA(cudaGetDeviceProperties(&prop, sl.device));
+    at.ctas_per_sm = nb;
+    at.sms = prop.multiProcessorCount;
+    at.cfg = C;
+  }
+  // tensor maps are cached per (slab, T, config, parity); the slot is shared with the first layout
+  if (sl.fused_T != T || sl.fused_cfg != (const void*)C) {
+    for (int p = 0; p < 2; ++p) FDB_TRY(f2_maps(f, d, *C, p, reinterpret_cast<Fused2Maps*>(sl.fused_maps[p])));
+    sl.fused_T = T;
+    sl.fused_cfg = (const void*)C;
+  }
+  Fused2Args a;
+  a.out = f.body(d, 1 - X);
+  a.n1 = f.geo.n[1];
+  a.n2 = f.geo.n[2];
+  a.ibeg = ibeg;
+  a.iend = iend;
+  a.njt = (int)((a.n1 + C->BJ - 1) / C->BJ);
+  a.nkt = (int)((a.n2 + C->BK - 1) / C->BK);
+  a.G = f.G;
+  a.c0 = k.c[0];
+  a.c1 = k.c[1];
+  a.c2 = k.c[2];
+  a.peer_out = peer_out;
+  a.peer_from = peer_from;
+  const int reserve = f.single() ? 0 : f2_env_int("FDB_COMM_SMS", 0);  // see kernels_fused.cu
+  int64_t grid_max = (int64_t)at.ctas_per_sm * (at.sms - reserve);
+  if (grid_max < 1) grid_max = 1;
+  const int64_t tiles = (int64_t)a.njt * a.nkt;
+  const int64_t planes = iend - ibeg;
+  int64_t ci = f2_env_int("FDB_TMA_CI", 0);
+  if (ci <= 0) {
+    // static round-robin: ceil(items / CTAs) rounds of (chunk + T warm-up planes) plane-steps
+    static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 24, 16, 8};
+    int64_t best_cost = -1;
+    for (int c : cand) {
+      const int64_t cc = c < planes ? c : planes;
+      const int64_t items = tiles * ((planes + cc - 1) / cc);
+      const int64_t cost = ((items + grid_max - 1) / grid_max) * (cc + T);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; ci = cc; }
+    }
+  }
+  if (ci > planes) ci = planes;
+  a.ci = (int)ci;
+  a.nwork = tiles * ((planes + ci - 1) / ci);
+  const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  C->kernel<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const Fused2Maps*>(sl.fused_maps[X]), a);
+  count_launch();
+  FDB_CUDA(cudaGetLastError());
+  return FDB_OK;
+}
+
+}  // namespace fdb

@@ -15,6 +15,7 @@ small = rng.random((24, 40, 260))
 big = rng.random((N, N, N)) if N <= 512 else None
 combos = os.environ.get("SWEEP_FUSED", "2:0,2:1,2:2,2:3,3:0,3:1,3:2,3:3,4:0,4:1,4:2").split(",")
 cis = [int(x) for x in os.environ.get("SWEEP_CIS", "0,64,128").split(",")]
+impl = os.environ.get("FDB_FUSED_IMPL", "default")  # 1: kernels_fused.cu, 2: kernels_fused2.cu (config tables differ)
 for combo in combos:
     T, cfg = (int(x) for x in combo.split(":"))
     os.environ["FDB_FUSED_CFG"] = str(cfg)
@@ -39,5 +40,5 @@ for combo in combos:
                 up.advect(nst, dt)
                 best = min(best, up.last_timing()["gpu_ms"] / nst)
             gcups = N ** 3 / best / 1e6
-            print(f"T={T} cfg={cfg} ci={ci:3d} N={N} parity={'ok' if ok else 'FAIL'} ms/step={best:.4f} "
+            print(f"impl={impl} T={T} cfg={cfg} ci={ci:3d} N={N} parity={'ok' if ok else 'FAIL'} ms/step={best:.4f} "
                   f"GCUPS={gcups:.1f} x_roofline={gcups * 16 / 6548.5:.3f}", flush=True)
