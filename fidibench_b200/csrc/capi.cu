@@ -33,7 +33,7 @@ struct fdb_stencil {
 
 namespace {
 
-constexpr int kDefaultFusedImpl = 1;  // which fused kernel runs (FDB_FUSED_IMPL overrides): kernels_fused.cu / _fused2.cu
+constexpr int kDefaultFusedImpl = 2;  // which fused kernel runs (FDB_FUSED_IMPL overrides): kernels_fused.cu / _fused2.cu
 
 int fused_impl() {
   const char* v = getenv("FDB_FUSED_IMPL");

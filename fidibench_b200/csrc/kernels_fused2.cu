@@ -321,18 +321,18 @@ const Fused2Config kF2_2[] = {
     make_fused2<Fused2Cfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),
 };
 const Fused2Config kF2_3[] = {
-    make_fused2<Fused2Cfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),
-    make_fused2<Fused2Cfg<3, 18, 6, 4>>("t3_cj18_r6_s4"),
+    make_fused2<Fused2Cfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // 835 / 867 GCUPS at 512^3 / 1024^3 (profiles/r01l_*)
+    make_fused2<Fused2Cfg<3, 18, 6, 4>>("t3_cj18_r6_s4"),  // six rows per thread: slower here (735 / 780)
     make_fused2<Fused2Cfg<3, 18, 6, 6>>("t3_cj18_r6_s6"),
     make_fused2<Fused2Cfg<3, 21, 7, 6>>("t3_cj21_r7_s6"),
     make_fused2<Fused2Cfg<3, 18, 3, 4, 64, 2>>("t3_cj18_r3_s4_bk64_2cta"),
     make_fused2<Fused2Cfg<3, 21, 3, 6>>("t3_cj21_r3_s6"),
     make_fused2<Fused2Cfg<3, 20, 5, 6>>("t3_cj20_r5_s6"),
-    make_fused2<Fused2Cfg<3, 24, 8, 6>>("t3_cj24_r8_s6"),
+    make_fused2<Fused2Cfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
 };
 const Fused2Config kF2_4[] = {
     make_fused2<Fused2Cfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
-    make_fused2<Fused2Cfg<4, 24, 8, 6>>("t4_cj24_r8_s6"),
+    make_fused2<Fused2Cfg<4, 18, 3, 4>>("t4_cj18_r3_s4"),
     make_fused2<Fused2Cfg<4, 18, 6, 6>>("t4_cj18_r6_s6"),
     make_fused2<Fused2Cfg<4, 20, 4, 6>>("t4_cj20_r4_s6"),
 };
