@@ -533,7 +533,7 @@ def main():
     peak, peak_src = measured_peak()
     # one sweep kernel advances `fuse` time steps of the slab; a remainder (T % fuse) runs the
     # single-step kernel.  achieved = algorithmic bytes of all launches / their total duration.
-    n_kernel_launches = (T // fuse + T % fuse) * args.steps
+    n_kernel_launches = (T // fuse + (1 if T % fuse else 0)) * args.steps   # remainders: [3,1] runs as [2,2], [2] as one sweep
     avg_launch_ms = ms / n_kernel_launches
     algo_bytes_per_launch = slab_cells * ALGO_BYTES_PER_UPDATE * T * args.steps / n_kernel_launches
     achieved = algo_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9

@@ -10,7 +10,7 @@ library without loading it first.
 import importlib
 
 _EXPORTS = {
-    "Upwind": "upwind", "Filter": "filter", "Comm": "comm", "slab_partition": "comm",
+    "Upwind": "upwind", "Filter": "filter", "Comm": "comm", "slab_partition": "comm", "CubeDecomp": "comm",
     "FdbError": "_lib", "device_count": "_lib", "launch_count": "_lib", "LIB_PATH": "_lib",
     "FDB_ROW_MAJOR": "_lib", "FDB_COL_MAJOR": "_lib", "FDB_INPUT": "_lib", "FDB_OUTPUT": "_lib",
     "FDB_KERNEL_AUTO": "_lib", "FDB_KERNEL_GENERIC": "_lib", "FDB_KERNEL_TMA": "_lib",

@@ -55,6 +55,9 @@ _SIGS = {
     "fdb_device_count": (i32, [p_i32]),
     "fdb_launch_count": (i32, [p_i64]),
     "fdb_slab_partition": (i32, [i64, i32, i32, p_i64, p_i64]),
+    "fdb_cube_decomp": (i32, [i32, i32, p_i64, p_i64]),
+    "fdb_cube_block": (i32, [i32, i32, p_i64, i32, p_i64, p_i64]),
+    "fdb_cube_neighbor": (i32, [i32, i32, p_i64, i32, p_i32, p_i32]),
     "fdb_comm_unique_id": (i32, [vp]),
     "fdb_comm_create": (i32, [i32, i32, vp, i32, p_vp]),
     "fdb_comm_rank": (i32, [vp, p_i32, p_i32]),

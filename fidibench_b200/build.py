@@ -19,7 +19,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libfidib200.so")
-SOURCES = ["runtime.cu", "kernels_generic.cu", "kernels_tma.cu", "kernels_fused.cu", "kernels_fused2.cu", "kernels_lapfused.cu", "capi.cu"]
+SOURCES = ["runtime.cu", "kernels_generic.cu", "kernels_tma.cu", "kernels_fused.cu", "kernels_lapfused.cu", "decomp.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "fdb_internal.h"), os.path.join(CSRC, "tma_ptx.cuh"), os.path.join(ROOT, "include", "fidib200.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

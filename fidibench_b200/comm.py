@@ -64,3 +64,45 @@ def slab_partition(n0: int, nparts: int, part: int) -> tuple[int, int]:
     lo, hi = C.c_int64(), C.c_int64()
     check(lib.fdb_slab_partition(n0, nparts, part, C.byref(lo), C.byref(hi)))
     return int(lo.value), int(hi.value)
+
+
+class CubeDecomp:
+    """Host-side mirror of the reference's `class CubeDecomp` (ref: cxx/CubeDecomp.h, CubeDecomp.cpp:11-131):
+    the process grid the reference would choose for `nprocs` ranks on `dims`, its blocks and neighbours.
+    The CUDA engines partition in slabs (slab_partition); this is for parity with MPI runs of the reference."""
+
+    def __init__(self):
+        self.nprocs, self.dims, self.decomp = 0, (), ()
+
+    def build(self, nprocs: int, dims) -> bool:
+        self.nprocs, self.dims = int(nprocs), tuple(int(d) for d in dims)
+        grid = (C.c_int64 * len(self.dims))()
+        rc = lib.fdb_cube_decomp(self.nprocs, len(self.dims), _lib.arr_i64(self.dims), grid)
+        if rc == _lib.FDB_E_DECOMP:
+            self.decomp = ()
+            return False
+        check(rc)
+        self.decomp = tuple(int(g) for g in grid)
+        return True
+
+    def getDecomp(self):
+        return self.decomp
+
+    def _block(self, rk: int):
+        nd = len(self.dims)
+        lo, hi = (C.c_int64 * nd)(), (C.c_int64 * nd)()
+        check(lib.fdb_cube_block(self.nprocs, nd, _lib.arr_i64(self.dims), int(rk), lo, hi))
+        return tuple(int(x) for x in lo), tuple(int(x) for x in hi)
+
+    def getBegIndices(self, rk: int):
+        return self._block(rk)[0]
+
+    def getEndIndices(self, rk: int):
+        return self._block(rk)[1]
+
+    def getNeighborRank(self, rk: int, direction) -> int:
+        nd = len(self.dims)
+        d = (C.c_int * nd)(*[int(x) for x in direction])
+        out = C.c_int()
+        check(lib.fdb_cube_neighbor(self.nprocs, nd, _lib.arr_i64(self.dims), int(rk), d, C.byref(out)))
+        return int(out.value)

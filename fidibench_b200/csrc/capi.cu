@@ -33,21 +33,11 @@ struct fdb_stencil {
 
 namespace {
 
-constexpr int kDefaultFusedImpl = 2;  // which fused kernel runs (FDB_FUSED_IMPL overrides): kernels_fused.cu / _fused2.cu
-
-int fused_impl() {
-  const char* v = getenv("FDB_FUSED_IMPL");
-  const int i = (v && *v) ? atoi(v) : kDefaultFusedImpl;
-  return i == 2 ? 2 : 1;
-}
-
 struct UpwindSweep : SweepLauncher {
   UpwindCoeffs k;
   bool tma = false;
-  int impl = 1;
   // depth = time steps this sweep advances (> 1: the fused temporal-blocking kernel)
   int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) override {
-    if (depth > 1 && impl == 2) return launch_upwind_fused2(*f, d, X, depth, ibeg, iend, k, s);
     if (depth > 1) return launch_upwind_fused(*f, d, X, depth, ibeg, iend, k, s);
     return tma ? launch_upwind_tma(*f, d, X, ibeg, iend, k, s)
                : launch_upwind_generic(*f, d, X, ibeg, iend, k, s);
@@ -57,7 +47,6 @@ struct UpwindSweep : SweepLauncher {
   int launch_push(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s, double* peer_out,
                   int64_t peer_from) override {
     if (!tma) return FDB_E_STATE;
-    if (depth > 1 && impl == 2) return launch_upwind_fused2(*f, d, X, depth, ibeg, iend, k, s, peer_out, peer_from);
     if (depth > 1) return launch_upwind_fused(*f, d, X, depth, ibeg, iend, k, s, peer_out, peer_from);
     return launch_upwind_tma(*f, d, X, ibeg, iend, k, s, peer_out, peer_from);
   }
@@ -496,10 +485,9 @@ int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTim
   int kern = FDB_KERNEL_GENERIC;
   FDB_TRY(fdb_upwind_get_kernel(h, &kern));
   sw.tma = (kern == FDB_KERNEL_TMA);
-  sw.impl = fused_impl();
   const int want = (h->fuse == 0) ? kAutoFuse : h->fuse;
   const int fuse = (sw.tma && want > 1 && upwind_fused_supported(*f, sw.k, want)) ? want : 1;
-  // plan: sweeps of `fuse` time steps, then the remainder
+  // plan: sweeps of `fuse` time steps, then the remainder (depths never increase along a plan)
   std::vector<int> depths;
   for (int64_t done = 0; done < numTimeSteps;) {
     const int64_t left = numTimeSteps - done;
@@ -507,6 +495,12 @@ int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTim
     if (t > 1 && !upwind_fused_supported(*f, sw.k, t)) t = 1;
     depths.push_back(t);
     done += t;
+  }
+  // a plan ending in [3, 1] runs as [2, 2]: the single-step kernel is the slowest per time step
+  if (depths.size() >= 2 && depths.back() == 1 && depths[depths.size() - 2] == 3 &&
+      upwind_fused_supported(*f, sw.k, 2)) {
+    depths[depths.size() - 2] = 2;
+    depths.back() = 2;
   }
   FDB_TRY(timing_begin(f));
   FDB_TRY(field_run_sweeps(f, &sw, depths.data(), (int)depths.size()));

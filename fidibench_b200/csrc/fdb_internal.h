@@ -199,11 +199,7 @@ bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k);
 bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T);
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                         cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0);
-// second shared-memory layout of the fused kernel (kernels_fused2.cu); FDB_FUSED_IMPL picks (1 / 2)
-bool upwind_fused2_supported(const Field& f, int T);
-int launch_upwind_fused2(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                         cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0);
-const char* upwind_fused2_name(int T);
+const char* upwind_fused_name(int T);
 // peer_out/peer_from: planes >= peer_from are also stored into the next slab's ghost planes
 int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                       cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0);

@@ -7,7 +7,6 @@
 // level 0 of planes i and i-1, level 2 from level 1 of planes i and i-1, ... up to level T,
 // which is the only one written back.  DRAM traffic per cell-update drops to ~16/T bytes.
 //
-//   * same TMA / mbarrier producer-consumer ring as the single-step kernel;
 //   * each consumer thread owns R rows x 2 cells of a CJ x CK compute tile and keeps plane
 //     i-1 of every level 0..T-1 in registers (T*R double2);
 //   * in-plane neighbours (j-1, k-1) of levels >= 1 travel through two ping-pong exchange
@@ -15,14 +14,26 @@
 //   * the tile computes T-1 halo rows/columns redundantly on its low sides (level s is valid
 //     from compute row/column s-1 on); only the BJ x BK interior of level T is stored, so
 //     output tiles stay 128-byte aligned along k;
-//   * periodic wrap: halo rows come from a separate TMA box at (j0-T) mod N1, the wrap
-//     columns of the first k-tile from boxes at N2-HKI; planes below the slab from the ghost
-//     tensor (depth T), which aliases the far planes on a single device;
 //   * a work item warms up on T extra planes below its chunk (levels become valid one plane
-//     after the other), nothing is stored for them.
+//     after the other), nothing is stored for them; planes below the slab come from the ghost
+//     tensor (depth T), which aliases the far planes on a single device.
+//
+// Shared-memory layout (the second one of round 1; the first addressed rows through per-row
+// selects and cost ~20 % more instructions, profiles/r01l_*):
+//   * ONE row pitch for the whole stage.  Rows are BKP = BK + 8 cells wide (global columns
+//     k0-8 .. k0+BK-1) so that two rows are a multiple of 128 bytes; the halo box holds HR rows
+//     (T rounded up to even) and the tile rows follow it directly.  Every shared-memory access of a
+//     consumer thread is `base + immediate`: no per-row selects, no per-plane address arithmetic.
+//   * the periodic wrap columns of the first k-tile (an 8-cell box at column N2-8) are copied into
+//     the zero-filled cells of the tile rows by the LOADER warp, which issues the TMA boxes and,
+//     a few planes later, hands each stage to the consumers; the consumers never see the wrap.
+//   * the exchange tiles use the same pitch and column offsets, with a spare row on top, so the
+//     stage and the exchange tile are addressed from the same thread base.
+//   * output addresses advance by one plane per iteration instead of being rebuilt.
 //
 // Arithmetic per level is exactly the single step's (separately rounded, reference order,
 // ref: upwind/cxx/upwind.cxx:72-80), so T fused steps are bit-identical to T single steps.
+// tests/host_model_fused.py restates the tile pipeline with numpy and is pinned to the oracle.
 #include "fdb_internal.h"
 #include "tma_ptx.cuh"
 
@@ -32,42 +43,42 @@ namespace {
 
 using namespace ptx;
 
-constexpr int align128(int x) { return (x + 127) / 128 * 128; }
+constexpr int fz_align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int T_, int CJ_, int R_, int STAGES_, bool SHFL_ = false, int BK_ = 128, int MINB_ = 1>
+template <int T_, int CJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1>
 struct FusedCfg {
-  static constexpr int T = T_, CJ = CJ_, R = R_, STAGES = STAGES_;
-  static constexpr bool SHFL = SHFL_;                  // k-1 neighbour by warp shuffle instead of LDS.64
-  static constexpr int BK = BK_;                       // output cells per tile row
-  static constexpr int MINB = MINB_;                   // CTAs per SM the register budget is sized for
-  static constexpr int HKC = 2 * (T / 2);              // redundant compute columns (even, >= T-1)
-  static constexpr int HKI = HKC + 2;                  // input halo columns (even, >= T)
-  static constexpr int CK = BK + HKC;                  // compute columns
-  static constexpr int TX = CK / 2;                    // threads per row
+  static constexpr int T = T_, CJ = CJ_, R = R_, STAGES = STAGES_, BK = BK_, MINB = MINB_;
+  static constexpr int HKC = 2 * (T / 2);          // redundant compute columns on the left (even, >= T-1)
+  static constexpr int CK = BK + HKC;              // compute columns: global k0-HKC .. k0+BK-1
+  static constexpr int TX = CK / 2;                // threads per row (2 cells each)
   static constexpr int TY = CJ / R;
   static constexpr int WORKERS = TX * TY;
   static constexpr int CONSUMERS = (WORKERS + 31) / 32 * 32;
   static constexpr int CONSUMER_WARPS = CONSUMERS / 32;
-  static constexpr int THREADS = CONSUMERS + 32;
-  static constexpr int BJ = CJ - (T - 1);              // output rows per tile
-  static constexpr int IN_ROWS = CJ + 1;               // input rows j0-T .. j0+BJ-1
-  static constexpr int BODY_ROWS = IN_ROWS - T;
-  static constexpr int BKH = BK + HKI;                 // input row pitch in doubles
-  static constexpr int ROW_BYTES = BKH * 8;
-  static constexpr int WROW_BYTES = HKI * 8;           // row pitch of the wrap-column area
-  static constexpr int HALO_OFF = 0;
-  static constexpr int BODY_OFF = align128(T * ROW_BYTES);
-  static constexpr int WH_OFF = align128(BODY_OFF + BODY_ROWS * ROW_BYTES);
-  static constexpr int WB_OFF = align128(WH_OFF + T * WROW_BYTES);
-  static constexpr int STAGE_BYTES = align128(WB_OFF + BODY_ROWS * WROW_BYTES);
-  static constexpr int TX_BYTES_MAIN = IN_ROWS * ROW_BYTES;
-  static constexpr int TX_BYTES_WRAP = IN_ROWS * WROW_BYTES;
-  static constexpr int XP = CK * 8;                    // exchange tile row pitch
-  static constexpr int X_BYTES = align128(CJ * XP);
+  static constexpr int THREADS = CONSUMERS + 32;   // + the loader warp
+  static constexpr int BJ = CJ - (T - 1);          // output rows per tile: global j0 .. j0+BJ-1
+  static constexpr int HR = (T + 1) / 2 * 2;       // halo rows loaded above the tile: global j0-HR .. j0-1
+  static constexpr int IN_ROWS = HR + BJ;          // stage rows; compute row q is stage row q + HR - T + 1
+  static constexpr int BKP = BK + 8;               // stage columns: global k0-8 .. k0+BK-1
+  static constexpr int LEFT = 8 - HKC;             // stage column of the first compute column
+  static constexpr int PITCH = BKP * 8;
+  static constexpr int BODY_OFF = HR * PITCH;
+  static constexpr int MAIN_BYTES = IN_ROWS * PITCH;
+  static constexpr int WPITCH = 64;                // wrap box rows: 8 cells, global columns N2-8 .. N2-1
+  static constexpr int W_OFF = fz_align128(MAIN_BYTES);
+  static constexpr int STAGE_BYTES = fz_align128(W_OFF + IN_ROWS * WPITCH);
+  static constexpr int TX_MAIN = IN_ROWS * PITCH;
+  static constexpr int TX_WRAP = IN_ROWS * WPITCH;
+  static constexpr int X_BYTES = fz_align128((CJ + 1) * PITCH);  // exchange tile: compute row q at row q + 1
   static constexpr int NX = (T > 1) ? 2 : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NX * X_BYTES + 2 * STAGES * 8 + 128;
-  static_assert(CJ % R == 0 && T >= 1 && HKC >= T - 1 && CJ > T, "bad fused tile");
-  static_assert(BKH <= 256 && BODY_ROWS <= 256, "TMA box limit");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NX * X_BYTES + 3 * STAGES * 8 + 128;
+  static constexpr int LAG = STAGES - 2;
+  static_assert(CJ % R == 0 && T >= 2 && T <= 4 && HKC >= T - 1 && CJ > T, "bad fused tile");
+  static_assert((HR * PITCH) % 128 == 0 && (HR * WPITCH) % 128 == 0, "misaligned TMA destination");
+  static_assert(BKP <= 256 && BJ <= 256, "TMA box limit");
+  static_assert(IN_ROWS <= 32, "one loader lane per stage row");
+  static_assert(STAGES >= 3, "the loader needs two stages of slack");
+  static_assert(THREADS <= 1024, "too many threads");
 };
 
 struct FusedArgs {
@@ -78,15 +89,19 @@ struct FusedArgs {
   int64_t nwork;
   int G;  // planes in the ghost tensor; local plane p < 0 is its plane G + p
   double c0, c1, c2;
-  // fused halo push: output planes p >= peer_from are ALSO stored through `peer_out`, the next
-  // slab's ghost planes mapped into this GPU's address space (NVLink peer stores); null = off
-  double* peer_out;
+  double* peer_out;   // planes p >= peer_from are also stored here (the next slab's ghost planes), or null
   int64_t peer_from;
+};
+
+// Tensor maps: m[0..3] over the local planes, m[4..7] over the ghost planes below; box shapes
+//   0/4: {BKP, HR} halo rows   1/5: {BKP, BJ} tile rows   2/6: {8, HR} wrap corner   3/7: {8, BJ} wrap columns
+struct FusedMaps {
+  CUtensorMap m[8];
 };
 
 // one upwind update of a cell (ref: upwind.cxx:72-80)
 __device__ __forceinline__ double upwind_cell(double ctr, double im1, double jm1, double km1, double c0,
-                                              double c1, double c2) {
+                                               double c1, double c2) {
   double t = ctr;
   t = __dsub_rn(t, __dmul_rn(c0, __dsub_rn(im1, ctr)));
   t = __dsub_rn(t, __dmul_rn(c1, __dsub_rn(jm1, ctr)));
@@ -94,11 +109,26 @@ __device__ __forceinline__ double upwind_cell(double ctr, double im1, double jm1
   return t;
 }
 
-// Tensor maps: m[0..3] over the local planes, m[4..7] over the ghost planes, box shapes
-//   0/4: {BKH, T}  halo rows      1/5: {BKH, BODY_ROWS}  tile rows
-//   2/6: {HKI, T}  wrap corner    3/7: {HKI, BODY_ROWS}  wrap columns
-struct FusedMaps {
-  CUtensorMap m[8];
+// position of the loader in the sequence of (work item, plane) pairs of this CTA
+template <class C>
+struct FusedCursor {
+  int64_t w, p, i1;
+  int kt, jt;
+  __device__ __forceinline__ void open(const FusedArgs& a) {
+    kt = (int)(w % a.nkt);
+    jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    p = i0 - C::T;
+  }
+  __device__ __forceinline__ bool valid(const FusedArgs& a) const { return w < a.nwork; }
+  __device__ __forceinline__ void next(const FusedArgs& a) {
+    if (++p >= i1) {
+      w += gridDim.x;
+      if (w < a.nwork) open(a);
+    }
+  }
 };
 
 template <class C>
@@ -107,13 +137,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
-  const uint32_t full = xbuf + C::NX * C::X_BYTES;
-  const uint32_t empty = full + C::STAGES * 8;
+  const uint32_t landed = xbuf + C::NX * C::X_BYTES;  // TMA bytes of the stage have arrived
+  const uint32_t full = landed + C::STAGES * 8;        // ... and its wrap columns are in place
+  const uint32_t empty = full + C::STAGES * 8;         // every consumer warp has read the stage
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
+  const int lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
       mbar_init(full + 8 * s, 1);
       mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
     }
@@ -122,37 +155,61 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   __syncthreads();
 
   if (warp == C::CONSUMER_WARPS) {
-    // ===================== producer warp =====================
-    if ((tid & 31) == 0) {
+    // ===================== loader warp (see kernels_lapfused.cu) =====================
+    if (lane == 0) {
 #pragma unroll
       for (int m = 0; m < 8; ++m) prefetch_tmap(&maps.m[m]);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
-        const int kt = (int)(w % a.nkt);
-        const int jt = (int)((w / a.nkt) % a.njt);
-        const int64_t ic = w / ((int64_t)a.nkt * a.njt);
-        const int64_t i0 = a.ibeg + ic * a.ci;
-        const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
-        const int kb = kt * C::BK - C::HKI;  // first input column (negative for the first k-tile)
-        const int j0 = jt * C::BJ;
-        const int jh = (j0 - C::T < 0) ? j0 - C::T + (int)a.n1 : j0 - C::T;  // periodic halo rows
-        const uint32_t bytes = C::TX_BYTES_MAIN + (kt == 0 ? C::TX_BYTES_WRAP : 0);
-        for (int64_t p = i0 - C::T; p < i1; ++p) {
-          mbar_wait(empty + 8 * stage, phase ^ 1);
-          const uint32_t st = smem + stage * C::STAGE_BYTES;
-          const uint32_t fb = full + 8 * stage;
-          const int g = (p < 0) ? 4 : 0;                 // ghost tensor below the slab
+    }
+    FusedCursor<C> ci, cf;  // issue / hand-over
+    ci.w = blockIdx.x;
+    if (ci.valid(a)) ci.open(a);
+    cf = ci;
+    int si = 0, sf = 0;
+    uint32_t phi = 0, phf = 0;
+    int ahead = 0;
+    while (cf.valid(a)) {
+      if (ci.valid(a)) {
+        mbar_wait(empty + 8 * si, phi ^ 1);
+        if (lane == 0) {
+          const uint32_t st = smem + si * C::STAGE_BYTES;
+          const uint32_t lb = landed + 8 * si;
+          const int kb = ci.kt * C::BK - 8;  // first stage column (negative for the first k-tile: zero fill)
+          const int j0 = ci.jt * C::BJ;
+          const int jh = (j0 - C::HR < 0) ? j0 - C::HR + (int)a.n1 : j0 - C::HR;  // periodic halo rows
+          const bool first_k = (ci.kt == 0);
+          const int64_t p = ci.p;
+          const int g = (p < 0) ? 4 : 0;  // ghost tensor below the slab
           const int pl = (p < 0) ? a.G + (int)p : (int)p;
-          mbar_expect_tx(fb, bytes);
-          tma_load_3d(st + C::HALO_OFF, &maps.m[g + 0], fb, kb, jh, pl);
-          tma_load_3d(st + C::BODY_OFF, &maps.m[g + 1], fb, kb, j0, pl);
-          if (kt == 0) {
-            tma_load_3d(st + C::WH_OFF, &maps.m[g + 2], fb, (int)a.n2 - C::HKI, jh, pl);
-            tma_load_3d(st + C::WB_OFF, &maps.m[g + 3], fb, (int)a.n2 - C::HKI, j0, pl);
+          mbar_expect_tx(lb, C::TX_MAIN + (first_k ? C::TX_WRAP : 0));
+          tma_load_3d(st, &maps.m[g + 0], lb, kb, jh, pl);
+          tma_load_3d(st + C::BODY_OFF, &maps.m[g + 1], lb, kb, j0, pl);
+          if (first_k) {
+            tma_load_3d(st + C::W_OFF, &maps.m[g + 2], lb, (int)a.n2 - 8, jh, pl);
+            tma_load_3d(st + C::W_OFF + C::HR * C::WPITCH, &maps.m[g + 3], lb, (int)a.n2 - 8, j0, pl);
           }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        ci.next(a);
+        if (++si == C::STAGES) { si = 0; phi ^= 1; }
+        ++ahead;
+      }
+      if (ahead > C::LAG || !ci.valid(a)) {
+        mbar_wait(landed + 8 * sf, phf);
+        if (cf.kt == 0 && lane < C::IN_ROWS) {
+          // columns -6 .. -1 of the tile rows <- columns N2-6 .. N2-1 (a sweep of T <= 4 steps reads
+          // back to column -(HKC + 1) >= -5)
+          const uint32_t st = smem + sf * C::STAGE_BYTES;
+          const double2 v0 = lds_v2(st + C::W_OFF + lane * C::WPITCH + 16);
+          const double2 v1 = lds_v2(st + C::W_OFF + lane * C::WPITCH + 32);
+          const double2 v2 = lds_v2(st + C::W_OFF + lane * C::WPITCH + 48);
+          sts_v2(st + lane * C::PITCH + 16, v0.x, v0.y);
+          sts_v2(st + lane * C::PITCH + 32, v1.x, v1.y);
+          sts_v2(st + lane * C::PITCH + 48, v2.x, v2.y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * sf);
+        cf.next(a);
+        if (++sf == C::STAGES) { sf = 0; phf ^= 1; }
+        --ahead;
       }
     }
     return;
@@ -163,16 +220,22 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   const int wid = worker ? tid : 0;
   const int tx = wid % C::TX;
   const int ty = wid / C::TX;
-  const int q0 = ty * C::R;  // first compute row of this thread
-  const int lane = tid & 31;
+  const int q0 = ty * C::R;  // first compute row of this thread (compute row q = global row j0-(T-1)+q)
   int stage = 0;
   uint32_t phase = 0;
   uint32_t xsel = 0;
   const double c0 = a.c0, c1 = a.c1, c2 = a.c2;
-  // exchange-tile addresses (levels >= 1): own cells, the row above, the cell to the left
-  const uint32_t x_own = q0 * C::XP + tx * 16;
-  const uint32_t x_up = (q0 == 0 ? 0 : (q0 - 1) * C::XP) + tx * 16;
-  const uint32_t x_km = q0 * C::XP + (tx == 0 ? 0 : tx * 16 - 8);
+  constexpr uint32_t P = C::PITCH;
+  // thread base: the row above the thread's first row, its own pair.  Exchange tile: compute row q
+  // at tile row q + 1; stage: compute row q at stage row q + HR - T + 1.
+  const uint32_t xt = q0 * P + (C::LEFT + 2 * tx) * 8;
+  const uint32_t tb = xt + (C::HR - C::T) * P;
+  // rows of this thread that belong to the output tile (compute rows T-1 .. CJ-1)
+  uint32_t rowmask = 0;
+#pragma unroll
+  for (int r = 0; r < C::R; ++r)
+    if (q0 + r >= C::T - 1) rowmask |= 1u << r;
+  const int64_t plane = a.n1 * a.n2;
 
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     const int kt = (int)(w % a.nkt);
@@ -180,12 +243,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     const int64_t ic = w / ((int64_t)a.nkt * a.njt);
     const int64_t i0 = a.ibeg + ic * a.ci;
     const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
-    const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;       // global column of this thread's first cell
-    const int64_t j = (int64_t)jt * C::BJ - (C::T - 1) + q0;       // global row of this thread's first row
+    const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;   // global column of this thread's first cell
+    const int64_t j = (int64_t)jt * C::BJ - (C::T - 1) + q0;   // global row of this thread's first row
     const bool store_cols = worker && (2 * tx >= C::HKC) && (k < a.n2);
-    // level-0 source of this thread's cells / left neighbour: main tile or wrap-column area
-    const bool own_wrap = (kt == 0) && (2 * tx + 2 < C::HKI);
-    const bool km_wrap = (kt == 0) && (2 * tx + 1 < C::HKI);
+    // rows of the output tile that exist (the last j-tile may be ragged)
+    uint32_t rmask = rowmask;
+#pragma unroll
+    for (int r = 0; r < C::R; ++r)
+      if (j + r >= a.n1) rmask &= ~(1u << r);
+    // offset of (plane p, row j, column k), advanced by one plane per iteration
+    int64_t ooff = ((i0 - C::T - 1) * a.n1 + j) * a.n2 + k;
 
     double2 carry[C::T][C::R];  // plane i-1 of levels 0..T-1
 #pragma unroll
@@ -194,33 +261,17 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
       for (int r = 0; r < C::R; ++r) carry[s][r] = make_double2(0.0, 0.0);
 
     for (int64_t p = i0 - C::T; p < i1; ++p) {
+      ooff += plane;
       mbar_wait(full + 8 * stage, phase);
-      const uint32_t st = smem + stage * C::STAGE_BYTES;
+      mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
+      const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
       double2 v[C::R];
       double km[C::R];
-      double2 up;
-      {
-        // stage row s = compute row + 1; rows 0..T-1 sit in the halo area
-        auto main_row = [&](int s) -> uint32_t {
-          return st + (s < C::T ? C::HALO_OFF + s * C::ROW_BYTES : C::BODY_OFF + (s - C::T) * C::ROW_BYTES);
-        };
-        auto wrap_row = [&](int s) -> uint32_t {
-          return st + (s < C::T ? C::WH_OFF + s * C::WROW_BYTES : C::WB_OFF + (s - C::T) * C::WROW_BYTES);
-        };
-        up = lds_v2((own_wrap ? wrap_row(q0) : main_row(q0)) + (2 * tx + 2) * 8);
+      double2 up = lds_v2(sb);
 #pragma unroll
-        for (int r = 0; r < C::R; ++r) {
-          const int s = q0 + r + 1;
-          v[r] = lds_v2((own_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 2) * 8);
-          if (C::SHFL) {
-            // the cell to the left is the previous lane's second cell; only a warp's first
-            // lane (and a row's first thread) reads it from shared memory
-            km[r] = __shfl_up_sync(0xffffffffu, v[r].y, 1);
-            if (lane == 0 || tx == 0) km[r] = lds_f64((km_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 1) * 8);
-          } else {
-            km[r] = lds_f64((km_wrap ? wrap_row(s) : main_row(s)) + (2 * tx + 1) * 8);
-          }
-        }
+      for (int r = 0; r < C::R; ++r) {
+        v[r] = lds_v2(sb + (1 + r) * P);
+        km[r] = lds_f64(sb + (1 + r) * P - 8);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + 8 * stage);
@@ -238,36 +289,30 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
         }
         if (s == C::T - 1) {
           if (p >= i0 && store_cols) {
-            double* orow = a.out + (p * a.n1 + j) * a.n2 + k;
-            double* prow = (a.peer_out != nullptr && p >= a.peer_from)
-                               ? a.peer_out + ((p - a.peer_from) * a.n1 + j) * a.n2 + k
-                               : nullptr;
+            double* orow = a.out + ooff;
+            const bool push = (a.peer_out != nullptr) && (p >= a.peer_from);
+            double* prow = a.peer_out + (ooff - a.peer_from * plane);
 #pragma unroll
             for (int r = 0; r < C::R; ++r) {
-              const int64_t jr = j + r;
-              if (q0 + r >= C::T - 1 && jr < a.n1) {
+              if ((rmask >> r) & 1u) {
                 st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
-                if (prow) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+                if (push) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
               }
             }
           }
         } else {
           // hand level s+1 of this plane to the neighbours through the exchange tile
-          const uint32_t xb = xbuf + xsel * C::X_BYTES;
+          const uint32_t xb = xbuf + xsel * C::X_BYTES + xt;
           xsel ^= 1;
           if (worker) {
 #pragma unroll
-            for (int r = 0; r < C::R; ++r) sts_v2(xb + x_own + r * C::XP, nv[r].x, nv[r].y);
-          }
-          if (C::SHFL) {
-#pragma unroll
-            for (int r = 0; r < C::R; ++r) km[r] = __shfl_up_sync(0xffffffffu, nv[r].y, 1);
+            for (int r = 0; r < C::R; ++r) sts_v2(xb + (1 + r) * P, nv[r].x, nv[r].y);
           }
           named_bar_sync(1, C::CONSUMERS);
-          up = lds_v2(xb + x_up);
+          up = lds_v2(xb);
 #pragma unroll
           for (int r = 0; r < C::R; ++r) {
-            if (!C::SHFL || lane == 0) km[r] = lds_f64(xb + x_km + r * C::XP);
+            km[r] = lds_f64(xb + (1 + r) * P - 8);
             v[r] = nv[r];
           }
         }
@@ -279,57 +324,40 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 // ---- configurations ---------------------------------------------------------------------
 typedef void (*FusedKernel)(const FusedMaps, const FusedArgs);
 struct FusedConfig {
-  int T, CJ, BJ, BK, BKH, HKI, body_rows, threads, smem;
+  int T, CJ, BJ, BK, BKP, HR, threads, smem;
   FusedKernel kernel;
   const char* name;
 };
 template <class C>
 constexpr FusedConfig make_fused(const char* name) {
-  return FusedConfig{C::T, C::CJ, C::BJ, C::BK, C::BKH, C::HKI, C::BODY_ROWS, C::THREADS, C::SMEM_BYTES,
-                     upwind3d_fused_kernel<C>, name};
+  return FusedConfig{C::T, C::CJ, C::BJ, C::BK, C::BKP, C::HR, C::THREADS, C::SMEM_BYTES,
+                      upwind3d_fused_kernel<C>, name};
 }
 // per T: index 0 is the default, the rest are tuning alternatives (env FDB_FUSED_CFG)
 const FusedConfig kFused2[] = {
-    make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),  // 750 GCUPS at 512^3 (DRAM-bound again)
-    make_fused<FusedCfg<2, 32, 4, 4>>("t2_cj32_r4_s4"),
-    make_fused<FusedCfg<2, 14, 2, 5>>("t2_cj14_r2_s5"),
-    make_fused<FusedCfg<2, 16, 4, 5>>("t2_cj16_r4_s5"),
-    make_fused<FusedCfg<2, 28, 4, 3>>("t2_cj28_r4_s3"),
-    make_fused<FusedCfg<2, 16, 2, 6>>("t2_cj16_r2_s6"),
-    make_fused<FusedCfg<2, 24, 3, 4>>("t2_cj24_r3_s4"),
+    make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),
+    make_fused<FusedCfg<2, 18, 6, 4>>("t2_cj18_r6_s4"),
     make_fused<FusedCfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),
-    make_fused<FusedCfg<2, 16, 2, 4, true>>("t2_cj16_r2_s4_shfl"),
-    make_fused<FusedCfg<2, 21, 3, 5, true>>("t2_cj21_r3_s5_shfl"),
+    make_fused<FusedCfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),
 };
 const FusedConfig kFused3[] = {
-    make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // round-1 best: 900 GCUPS at 512^3 / 1024^3
-    make_fused<FusedCfg<3, 16, 2, 4>>("t3_cj16_r2_s4"),
-    make_fused<FusedCfg<3, 14, 2, 5>>("t3_cj14_r2_s5"),
-    make_fused<FusedCfg<3, 28, 4, 3>>("t3_cj28_r4_s3"),
-    make_fused<FusedCfg<3, 16, 4, 4>>("t3_cj16_r4_s4"),
-    make_fused<FusedCfg<3, 21, 3, 3>>("t3_cj21_r3_s3"),
-    make_fused<FusedCfg<3, 21, 3, 5>>("t3_cj21_r3_s5"),
-    make_fused<FusedCfg<3, 24, 3, 4>>("t3_cj24_r3_s4"),
+    make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // 835 / 867 GCUPS at 512^3 / 1024^3 (profiles/r01l_*)
+    make_fused<FusedCfg<3, 18, 6, 4>>("t3_cj18_r6_s4"),  // six rows per thread: slower here (735 / 780)
+    make_fused<FusedCfg<3, 18, 6, 6>>("t3_cj18_r6_s6"),
+    make_fused<FusedCfg<3, 21, 7, 6>>("t3_cj21_r7_s6"),
+    make_fused<FusedCfg<3, 18, 3, 4, 64, 2>>("t3_cj18_r3_s4_bk64_2cta"),
+    make_fused<FusedCfg<3, 21, 3, 6>>("t3_cj21_r3_s6"),
+    make_fused<FusedCfg<3, 20, 5, 6>>("t3_cj20_r5_s6"),
     make_fused<FusedCfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
-    make_fused<FusedCfg<3, 21, 3, 4, true>>("t3_cj21_r3_s4_shfl"),
-    make_fused<FusedCfg<3, 16, 2, 4, true>>("t3_cj16_r2_s4_shfl"),
-    make_fused<FusedCfg<3, 18, 3, 4, false, 64, 2>>("t3_cj18_r3_s4_bk64_2cta"),
-    make_fused<FusedCfg<3, 18, 3, 4, true, 64, 2>>("t3_cj18_r3_s4_bk64_2cta_shfl"),
-    make_fused<FusedCfg<3, 21, 3, 3, false, 64, 2>>("t3_cj21_r3_s3_bk64_2cta"),
-    make_fused<FusedCfg<3, 21, 3, 5, true>>("t3_cj21_r3_s5_shfl"),
 };
 const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
-    make_fused<FusedCfg<4, 16, 2, 4>>("t4_cj16_r2_s4"),
-    make_fused<FusedCfg<4, 14, 2, 4>>("t4_cj14_r2_s4"),
-    make_fused<FusedCfg<4, 28, 4, 3>>("t4_cj28_r4_s3"),
-    make_fused<FusedCfg<4, 16, 4, 4>>("t4_cj16_r4_s4"),
-    make_fused<FusedCfg<4, 21, 3, 3>>("t4_cj21_r3_s3"),
-    make_fused<FusedCfg<4, 21, 3, 4, true>>("t4_cj21_r3_s4_shfl"),
-    make_fused<FusedCfg<4, 16, 2, 4, true>>("t4_cj16_r2_s4_shfl"),
+    make_fused<FusedCfg<4, 18, 3, 4>>("t4_cj18_r3_s4"),
+    make_fused<FusedCfg<4, 18, 6, 6>>("t4_cj18_r6_s6"),
+    make_fused<FusedCfg<4, 20, 4, 6>>("t4_cj20_r4_s6"),
 };
 
-const FusedConfig* fused_table(int T, int* count) {
+const FusedConfig* fz_table(int T, int* count) {
   switch (T) {
     case 2: *count = sizeof(kFused2) / sizeof(kFused2[0]); return kFused2;
     case 3: *count = sizeof(kFused3) / sizeof(kFused3[0]); return kFused3;
@@ -339,16 +367,16 @@ const FusedConfig* fused_table(int T, int* count) {
   return nullptr;
 }
 
-int env_int2(const char* name, int dflt) {
+int fz_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
 
-const FusedConfig* fused_pick(int T) {
+const FusedConfig* fz_pick(int T) {
   int n = 0;
-  const FusedConfig* tab = fused_table(T, &n);
+  const FusedConfig* tab = fz_table(T, &n);
   if (!tab) return nullptr;
-  int c = env_int2("FDB_FUSED_CFG", 0);
+  int c = fz_env_int("FDB_FUSED_CFG", 0);
   if (c < 0 || c >= n) c = 0;
   return &tab[c];
 }
@@ -358,7 +386,19 @@ struct FusedAttr {
   int ctas_per_sm = 1;
   int sms = 148;
 };
-FusedAttr g_fused_attr[16][kMaxFuse + 1];
+FusedAttr g_fz_attr[16][kMaxFuse + 1];
+
+int fz_maps(const Field& f, int d, const FusedConfig& C, int p, FusedMaps* out) {
+  const Slab& s = f.slabs[d];
+  const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
+  const double* base[2] = {f.body(d, p), f.ghost_lo(d, p)};
+  const int64_t planes[2] = {s.nloc(), f.G};
+  const int boxes[4][2] = {{C.BKP, C.HR}, {C.BKP, C.BJ}, {8, C.HR}, {8, C.BJ}};
+  for (int t = 0; t < 2; ++t)
+    for (int b = 0; b < 4; ++b)
+      FDB_TRY(encode_tensor_map_3d(&out->m[4 * t + b], base[t], n2, n1, planes[t], boxes[b][0], boxes[b][1]));
+  return FDB_OK;
+}
 
 }  // namespace
 
@@ -371,29 +411,20 @@ bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T) {
   if (f.geo.n[1] < 8 || f.geo.n[2] < 16) return false;
   for (const Slab& s : f.slabs)
     if (s.nloc() < T) return false;
-  return true;
+  return fz_pick(T) != nullptr;
 }
 
-// tensor maps of slab d for fuse depth T, buffer parity p (encoded on first use)
-static int fused_maps(const Field& f, int d, int T, const FusedConfig& C, int p, FusedMaps* out) {
-  const Slab& s = f.slabs[d];
-  const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
-  const double* body = f.body(d, p);
-  const double* glo = f.ghost_lo(d, p);
-  const int boxes[4][2] = {{C.BKH, T}, {C.BKH, C.body_rows}, {C.HKI, T}, {C.HKI, C.body_rows}};
-  for (int b = 0; b < 4; ++b) {
-    FDB_TRY(encode_tensor_map_3d(&out->m[b], body, n2, n1, s.nloc(), boxes[b][0], boxes[b][1]));
-    FDB_TRY(encode_tensor_map_3d(&out->m[4 + b], glo, n2, n1, f.G, boxes[b][0], boxes[b][1]));
-  }
-  return FDB_OK;
+const char* upwind_fused_name(int T) {
+  const FusedConfig* C = fz_pick(T);
+  return C ? C->name : "";
 }
 
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                        cudaStream_t s, double* peer_out, int64_t peer_from) {
+                         cudaStream_t s, double* peer_out, int64_t peer_from) {
   if (iend <= ibeg) return FDB_OK;
   Slab& sl = f.slabs[d];
-  FusedAttr& at = g_fused_attr[sl.device & 15][T];
-  const FusedConfig* C = fused_pick(T);
+  FusedAttr& at = g_fz_attr[sl.device & 15][T];
+  const FusedConfig* C = fz_pick(T);
   if (!C) return set_error(FDB_E_INVALID, "no fused kernel for %d steps per sweep", T);
   if (at.cfg != C) {
     FDB_CUDA(cudaFuncSetAttribute(C->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
@@ -408,8 +439,7 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   }
   // tensor maps are cached per (slab, T, config, parity)
   if (sl.fused_T != T || sl.fused_cfg != (const void*)C) {
-    for (int p = 0; p < 2; ++p)
-      FDB_TRY(fused_maps(f, d, T, *C, p, reinterpret_cast<FusedMaps*>(sl.fused_maps[p])));
+    for (int p = 0; p < 2; ++p) FDB_TRY(fz_maps(f, d, *C, p, reinterpret_cast<FusedMaps*>(sl.fused_maps[p])));
     sl.fused_T = T;
     sl.fused_cfg = (const void*)C;
   }
@@ -427,19 +457,22 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   a.c2 = k.c[2];
   a.peer_out = peer_out;
   a.peer_from = peer_from;
-  // The direct halo transport runs on copy engines and needs no SM.  With the NCCL transport
-  // the send/recv kernels must find free SMs while the persistent interior kernel runs:
-  // FDB_COMM_SMS leaves some unoccupied (mind the extra round a smaller grid can cost).
-  const int reserve = f.single() ? 0 : env_int2("FDB_COMM_SMS", 0);
+  const int reserve = f.single() ? 0 : fz_env_int("FDB_COMM_SMS", 0);  // SMs left free for NCCL halo kernels
   int64_t grid_max = (int64_t)at.ctas_per_sm * (at.sms - reserve);
   if (grid_max < 1) grid_max = 1;
   const int64_t tiles = (int64_t)a.njt * a.nkt;
   const int64_t planes = iend - ibeg;
-  int64_t ci = env_int2("FDB_TMA_CI", 0);
+  int64_t ci = fz_env_int("FDB_TMA_CI", 0);
   if (ci <= 0) {
-    // every work item warms up on T extra planes: favour long chunks
-    ci = 128;
-    while (ci > 8 && tiles * ((planes + ci - 1) / ci) < 2 * grid_max) ci /= 2;
+    // static round-robin: ceil(items / CTAs) rounds of (chunk + T warm-up planes) plane-steps
+    static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 24, 16, 8};
+    int64_t best_cost = -1;
+    for (int c : cand) {
+      const int64_t cc = c < planes ? c : planes;
+      const int64_t items = tiles * ((planes + cc - 1) / cc);
+      const int64_t cost = ((items + grid_max - 1) / grid_max) * (cc + T);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; ci = cc; }
+    }
   }
   if (ci > planes) ci = planes;
   a.ci = (int)ci;

@@ -74,6 +74,15 @@ int fdb_launch_count(int64_t *count);
  * nparts divides n0 (the reference has the same requirement, CubeDecomp.cpp:26-28). */
 int fdb_slab_partition(int64_t n0, int nparts, int part, int64_t *lo, int64_t *hi);
 
+/* The reference's own process-grid chooser, restated on the host (ref: CubeDecomp::build /
+ * computeOptimalDecomp / getBegIndices / getEndIndices / getNeighborRank, cxx/CubeDecomp.cpp:11-131), for
+ * callers that want its block decomposition (e.g. to compare with an MPI run): ndims in 1..3.
+ * grid[ndims] <- processes per axis; FDB_E_DECOMP when no divisor tuple multiplies to nprocs
+ * (ref: Filter.cpp:27-34).  Ranks are row-major over the grid; neighbours are periodic. */
+int fdb_cube_decomp(int nprocs, int ndims, const int64_t *dims, int64_t *grid);
+int fdb_cube_block(int nprocs, int ndims, const int64_t *dims, int rank, int64_t *lo, int64_t *hi);
+int fdb_cube_neighbor(int nprocs, int ndims, const int64_t *dims, int rank, const int *dir, int *neighbor);
+
 /* ---- communicator for one-process-per-GPU runs --------------------------- */
 typedef struct fdb_comm fdb_comm;
 #define FDB_COMM_ID_BYTES 128

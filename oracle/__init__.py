@@ -218,6 +218,20 @@ class _Ref:
         ok = self.F.fdb_ref_cubedecomp(int(nprocs), len(dims), self._ll(dims), dec)
         return tuple(int(x) for x in dec) if ok else None
 
+    def cubedecomp_rank(self, nprocs, dims, rank, dirs):
+        """(lo, hi, neighbour ranks) of `rank` from CubeDecomp::getBegIndices/getEndIndices/getNeighborRank."""
+        nd = len(dims)
+        lo, hi = (C.c_longlong * nd)(), (C.c_longlong * nd)()
+        d = np.ascontiguousarray(dirs, dtype=np.int32).reshape(-1, nd)
+        nbr = np.zeros(d.shape[0], dtype=np.int32)
+        fn = self.F.fdb_ref_cubedecomp_rank
+        fn.restype = C.c_int
+        ok = fn(int(nprocs), nd, self._ll(dims), int(rank), lo, hi, d.shape[0], d.ctypes.data_as(_c_int_p),
+                nbr.ctypes.data_as(_c_int_p))
+        if not ok:
+            return None
+        return tuple(int(x) for x in lo), tuple(int(x) for x in hi), tuple(int(x) for x in nbr)
+
     def upwind_exe(self) -> str:
         return os.path.join(self.dir, "upwindCxx")
 

@@ -133,6 +133,22 @@ int fdb_ref_cubedecomp(int nprocs, int ndims, const long long *dims, long long *
   return 1;
 }
 
+/* the rest of CubeDecomp's surface for one rank: getBegIndices / getEndIndices (CubeDecomp.cpp:88-109) and
+ * getNeighborRank for every direction in dirs (ndir x ndims, CubeDecomp.cpp:111-131). Returns 1 if valid. */
+int fdb_ref_cubedecomp_rank(int nprocs, int ndims, const long long *dims, int rank, long long *lo, long long *hi,
+                            int ndir, const int *dirs, int *nbr) {
+  std::vector<size_t> gd(dims, dims + ndims);
+  CubeDecomp d;
+  if (!d.build(nprocs, gd)) return 0;
+  std::vector<size_t> b = d.getBegIndices(rank), e = d.getEndIndices(rank);
+  for (int j = 0; j < ndims; ++j) { lo[j] = (long long)b[j]; hi[j] = (long long)e[j]; }
+  for (int k = 0; k < ndir; ++k) {
+    std::vector<int> dir(dirs + k * ndims, dirs + (k + 1) * ndims);
+    nbr[k] = d.getNeighborRank(rank, dir);
+  }
+  return 1;
+}
+
 int fdb_ref_laplacian_main(int, char **);
 int fdb_ref_upwindmpi_main(int, char **);
 int fdb_ref_laplacian_cli(int argc, char **argv) { return fdb_ref_laplacian_main(argc, argv); }

@@ -100,6 +100,27 @@ def main():
     # CubeDecomp's choices, for the record (we replace it with slabs)
     dec = {f"p{p}": np.array(r.cubedecomp(p, [128] * 3) or (0, 0, 0)) for p in (1, 2, 3, 4, 8, 16)}
     np.savez_compressed(os.path.join(HERE, "cubedecomp_128.npz"), **dec)
+
+    # the whole CubeDecomp surface on a spread of grids: chosen process grid, every rank's block and its
+    # neighbours in a fixed set of directions (fdb_cube_* must reproduce all of it, quirks included)
+    cases = []
+    for dims in ([128] * 3, [96, 64, 128], [12, 18], [8000, 8000], [30], [1, 8, 8], [64, 1, 64], [7, 5, 3], [1]):
+        for p in (1, 2, 3, 4, 6, 8, 12, 16, 32, 64):
+            cases.append((p, dims))
+    rec = []
+    for p, dims in cases:
+        nd = len(dims)
+        dirs = [[(1 if a == j else 0) * s for a in range(nd)] for j in range(nd) for s in (1, -1)] + [[1] * nd, [-1] * nd]
+        dec = r.cubedecomp(p, dims)
+        row = dict(nprocs=p, dims=list(dims), decomp=list(dec) if dec else None, ranks=[])
+        if dec:
+            for rk in sorted({0, 1 % p, p // 2, p - 1}):
+                lo, hi, nb = r.cubedecomp_rank(p, dims, rk, dirs)
+                row["ranks"].append(dict(rank=rk, lo=list(lo), hi=list(hi), dirs=dirs, nbr=list(nb)))
+        rec.append(row)
+    import json
+    with open(os.path.join(HERE, "cubedecomp_cases.json"), "w") as fh:
+        json.dump(rec, fh)
     print("golden fixtures written to", HERE)
 
 

@@ -1,4 +1,4 @@
-"""Host model of upwind3d_fused2_kernel (fidibench_b200/csrc/kernels_fused2.cu): same constants,
+"""Host model of upwind3d_fused_kernel (fidibench_b200/csrc/kernels_fused.cu): same constants,
 shared-memory offsets and thread-to-cell mapping as the CUDA kernel, numpy instead of threads (see
 tests/host_model_lapfused.py for the idea).  Memory nobody wrote is NaN."""
 from __future__ import annotations
@@ -9,7 +9,7 @@ from host_model_lapfused import align128, tma_box
 
 
 class Cfg:
-    """Fused2Cfg<T, CJ, R, STAGES, BK>"""
+    """FusedCfg<T, CJ, R, STAGES, BK>"""
 
     def __init__(self, T: int, CJ: int, R: int, BK: int = 128):
         self.T, self.CJ, self.R, self.BK = T, CJ, R, BK

@@ -1,0 +1,65 @@
+"""fdb_cube_* (the host restatement of the reference's CubeDecomp, csrc/decomp.cu) against the reference's
+own answers: the committed fixture (tests/golden/cubedecomp_cases.json, written by make_golden.py from
+oracle/_ref) and, where oracle/_ref is built, the live reference on more grids.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, SEED
+
+
+def check_case(fb, row):
+    d = fb.CubeDecomp()
+    ok = d.build(row["nprocs"], row["dims"])
+    if row["decomp"] is None:
+        assert not ok and d.getDecomp() == ()      # ref: Filter.cpp:27-34 reports "No valid domain decomposition"
+        return
+    assert ok and list(d.getDecomp()) == row["decomp"], row
+    for rk in row["ranks"]:
+        assert list(d.getBegIndices(rk["rank"])) == rk["lo"], (row, rk)
+        assert list(d.getEndIndices(rk["rank"])) == rk["hi"], (row, rk)
+        for direction, nb in zip(rk["dirs"], rk["nbr"]):
+            assert d.getNeighborRank(rk["rank"], direction) == nb, (row, rk, direction)
+
+
+def test_cube_decomp_matches_the_reference_fixture(fb):
+    with open(os.path.join(GOLDEN, "cubedecomp_cases.json")) as fh:
+        rows = json.load(fh)
+    assert len(rows) >= 80 and any(r["decomp"] is None for r in rows)
+    for row in rows:
+        check_case(fb, row)
+    # the survey's probes: candidate #0 is skipped whenever there are two or more
+    by = {(r["nprocs"], tuple(r["dims"])): r["decomp"] for r in rows}
+    assert by[(2, (128, 128, 128))] == [1, 2, 1] and by[(16, (128, 128, 128))] == [4, 2, 2]
+    assert by[(3, (128, 128, 128))] is None
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built here")
+def test_cube_decomp_matches_the_live_reference_on_random_grids(fb):
+    rng = np.random.default_rng(SEED + 40)
+    r = oracle.ref()
+    for _ in range(150):
+        nd = int(rng.integers(1, 4))
+        dims = [int(x) for x in rng.integers(1, 49, size=nd)]
+        p = int(rng.integers(1, 25))
+        dec = r.cubedecomp(p, dims)
+        dirs = [[int(x) for x in rng.integers(-1, 2, size=nd)] for _ in range(4)]
+        row = dict(nprocs=p, dims=dims, decomp=list(dec) if dec else None, ranks=[])
+        if dec:
+            for rk in {0, p - 1, int(rng.integers(0, p))}:
+                lo, hi, nb = r.cubedecomp_rank(p, dims, rk, dirs)
+                row["ranks"].append(dict(rank=rk, lo=list(lo), hi=list(hi), dirs=dirs, nbr=list(nb)))
+        check_case(fb, row)
+
+
+def test_cube_decomp_argument_errors(fb):
+    from fidibench_b200 import _lib
+    import ctypes as C
+    grid = (C.c_int64 * 3)()
+    assert _lib.lib.fdb_cube_decomp(0, 3, _lib.arr_i64([8, 8, 8]), grid) == _lib.FDB_E_INVALID
+    assert _lib.lib.fdb_cube_decomp(2, 4, _lib.arr_i64([8, 8, 8, 8]), grid) == _lib.FDB_E_INVALID
+    assert _lib.lib.fdb_cube_decomp(3, 3, _lib.arr_i64([8, 8, 8]), grid) == _lib.FDB_E_DECOMP
+    assert b"No valid domain decomposition" in _lib.lib.fdb_last_error()

@@ -1,11 +1,11 @@
-"""CPU check of the second fused-upwind layout: the host model that mirrors upwind3d_fused2_kernel
-(tests/host_model_fused2.py) must equal T oracle time steps bit for bit -- ragged tiles on both
+"""CPU check of the fused upwind tile pipeline: the host model that mirrors upwind3d_fused_kernel
+(tests/host_model_fused.py) must equal T oracle time steps bit for bit -- ragged tiles on both
 in-plane axes, ragged plane chunks, single slab and slab of a ring."""
 import numpy as np
 import pytest
 
 import oracle
-from host_model_fused2 import Cfg, fused_steps
+from host_model_fused import Cfg, fused_steps
 
 SEED = 20261017
 

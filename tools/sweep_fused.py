@@ -15,7 +15,7 @@ small = rng.random((24, 40, 260))
 big = rng.random((N, N, N)) if N <= 512 else None
 combos = os.environ.get("SWEEP_FUSED", "2:0,2:1,2:2,2:3,3:0,3:1,3:2,3:3,4:0,4:1,4:2").split(",")
 cis = [int(x) for x in os.environ.get("SWEEP_CIS", "0,64,128").split(",")]
-impl = os.environ.get("FDB_FUSED_IMPL", "default")  # 1: kernels_fused.cu, 2: kernels_fused2.cu (config tables differ)
+impl = "r01l-layout"
 for combo in combos:
     T, cfg = (int(x) for x in combo.split(":"))
     os.environ["FDB_FUSED_CFG"] = str(cfg)
