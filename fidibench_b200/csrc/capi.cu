@@ -18,6 +18,11 @@ struct fdb_upwind {
   int64_t num_cells[3] = {1, 1, 1};
   int kernel = FDB_KERNEL_AUTO;
   int fuse = 0;  // time steps per sweep; 0 = auto (kAutoFuse when the fused kernel can run)
+  // Axes (internal) along which the device holds the field MIRRORED: a negative velocity along an axis is
+  // a positive one on the mirrored grid, with the same coefficient bits ((dt*-v)*-1 == (dt*v)*+1), so the
+  // tiled kernels (written for the upwind direction -1) run every sign.  Single-slab handles only.
+  bool flip[3] = {false, false, false};
+  bool any_flip = false;
 };
 
 struct fdb_stencil {
@@ -72,9 +77,10 @@ void upwind_coeffs(const fdb_upwind* h, double dt, UpwindCoeffs* k) {
   for (int a = 0; a < 3; ++a) { k->c[a] = 0.0; k->up[a] = -1; k->active[a] = false; }
   for (int j = 0; j < g.ndims; ++j) {
     const int a = g.axis_of[j];
-    const int up = (h->velocity[j] < 0.) ? +1 : -1;
+    const double v = h->flip[a] ? -h->velocity[j] : h->velocity[j];  // the velocity on the (mirrored) device grid
+    const int up = (v < 0.) ? +1 : -1;
     const double delta = h->lengths[j] / (double)(size_t)h->num_cells[j];
-    k->c[a] = dt * h->velocity[j] * up / delta;
+    k->c[a] = dt * v * up / delta;
     k->up[a] = up;
     k->active[a] = true;
   }
@@ -108,6 +114,31 @@ int timing_collect(Field* f) {
   return FDB_OK;
 }
 
+// where the ctor's cell 0 (upwind.cxx:48) sits on the device grid
+int64_t upwind_mirrored_cell0(const fdb_upwind* h, const Geometry& g) {
+  int64_t cell = 0;
+  const int64_t stride[3] = {g.n[1] * g.n[2], g.n[2], 1};
+  for (int a = 0; a < 3; ++a)
+    if (h->flip[a]) cell += (g.n[a] - 1) * stride[a];
+  return cell;
+}
+
+// host data lands in the spare buffer and is mirrored into the current one (and back for downloads)
+int upwind_upload(fdb_upwind* h, const double* host_global, const double* host_slab, bool async) {
+  Field* f = &h->field;
+  if (!h->any_flip) return field_upload(f, f->cur, host_global, host_slab, async);
+  const int cur = f->cur;
+  FDB_TRY(field_upload(f, 1 - cur, host_global, host_slab, async));  // (publishes the spare buffer for a moment)
+  return field_mirror(f, 1 - cur, cur, h->flip, /*publish=*/true);
+}
+
+int upwind_download(fdb_upwind* h, double* host_global, double* host_slab) {
+  Field* f = &h->field;
+  if (!h->any_flip) return field_download(f, f->cur, host_global, host_slab);
+  FDB_TRY(field_mirror(f, f->cur, 1 - f->cur, h->flip, /*publish=*/false));  // the spare buffer holds no live data
+  return field_download(f, 1 - f->cur, host_global, host_slab);
+}
+
 int upwind_common_create(int ndims, const int64_t* numCells, const double* velocity,
                          const double* lengths, int ngpus, fdb_comm* comm, fdb_upwind** out) {
   if (!out) return set_error(FDB_E_INVALID, "null output handle");
@@ -132,8 +163,20 @@ int upwind_common_create(int ndims, const int64_t* numCells, const double* veloc
   const int nparts = comm ? comm->nranks : (ngpus > 0 ? ngpus : 1);
   const int64_t nloc = geo.n[0] / nparts;
   const int G = (int)std::max<int64_t>(1, std::min<int64_t>(kMaxFuse, nloc));
+  // mirror the axes with a negative velocity when that lets the tiled kernels run (one slab, 3-D, the
+  // kernels' shape requirements); FDB_NO_FLIP=1 keeps the generic kernel for them
+  {
+    const char* nf = getenv("FDB_NO_FLIP");
+    const bool allow = !(nf && *nf && atoi(nf) != 0) && nparts == 1 && ndims == 3 && geo.n[2] % 2 == 0 &&
+                       geo.n[2] >= 4 && geo.n[1] >= 2;
+    for (int j = 0; j < ndims && allow; ++j)
+      if (velocity[j] < 0. && geo.n[geo.axis_of[j]] > 1) {
+        h->flip[geo.axis_of[j]] = true;
+        h->any_flip = true;
+      }
+  }
   int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/1);
-  if (rc == FDB_OK) rc = field_fill_delta(&h->field, 0);
+  if (rc == FDB_OK) rc = field_fill_delta(&h->field, 0, upwind_mirrored_cell0(h, geo));
   if (rc == FDB_OK) rc = field_sync(&h->field);
   if (rc != FDB_OK) {
     field_destroy(&h->field);
@@ -385,7 +428,7 @@ int fdb_upwind_local_range(const fdb_upwind* h, int64_t* lo, int64_t* hi) {
 int fdb_upwind_set_field(fdb_upwind* h, const double* host_field) {
   FDB_GUARD_BEGIN
   if (!h || !host_field) return set_error(FDB_E_INVALID, "null argument");
-  FDB_TRY(field_upload(&h->field, h->field.cur, host_field, nullptr));
+  FDB_TRY(upwind_upload(h, host_field, nullptr, false));
   return field_sync(&h->field);
   FDB_GUARD_END
 }
@@ -393,7 +436,7 @@ int fdb_upwind_set_field(fdb_upwind* h, const double* host_field) {
 int fdb_upwind_set_slab(fdb_upwind* h, const double* host_slab) {
   FDB_GUARD_BEGIN
   if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
-  FDB_TRY(field_upload(&h->field, h->field.cur, nullptr, host_slab));
+  FDB_TRY(upwind_upload(h, nullptr, host_slab, false));
   return field_sync(&h->field);
   FDB_GUARD_END
 }
@@ -401,14 +444,14 @@ int fdb_upwind_set_slab(fdb_upwind* h, const double* host_slab) {
 int fdb_upwind_set_slab_async(fdb_upwind* h, const double* host_slab) {
   FDB_GUARD_BEGIN
   if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
-  return field_upload(&h->field, h->field.cur, nullptr, host_slab, /*async=*/true);
+  return upwind_upload(h, nullptr, host_slab, /*async=*/true);
   FDB_GUARD_END
 }
 
 int fdb_upwind_reset(fdb_upwind* h) {
   FDB_GUARD_BEGIN
   if (!h) return set_error(FDB_E_INVALID, "null handle");
-  FDB_TRY(field_fill_delta(&h->field, h->field.cur));
+  FDB_TRY(field_fill_delta(&h->field, h->field.cur, upwind_mirrored_cell0(h, h->field.geo)));
   return field_sync(&h->field);
   FDB_GUARD_END
 }
@@ -445,7 +488,8 @@ int fdb_upwind_set_kernel(fdb_upwind* h, int kernel) {
     upwind_coeffs(h, 1.0, &k);
     if (!upwind_tma_supported(h->field, k))
       return set_error(FDB_E_INVALID,
-                       "the TMA kernel needs a 3-D grid, non-negative velocities and an even last extent");
+                       "the TMA kernel needs a 3-D grid, an even last extent and -- on several slabs -- "
+                       "non-negative velocities");
   }
   h->kernel = kernel;
   return FDB_OK;
@@ -545,14 +589,14 @@ int fdb_upwind_std(fdb_upwind* h, double* stddev) {
 int fdb_upwind_get_field(fdb_upwind* h, double* host_field) {
   FDB_GUARD_BEGIN
   if (!h || !host_field) return set_error(FDB_E_INVALID, "null argument");
-  return field_download(&h->field, h->field.cur, host_field, nullptr);
+  return upwind_download(h, host_field, nullptr);
   FDB_GUARD_END
 }
 
 int fdb_upwind_get_slab(fdb_upwind* h, double* host_slab) {
   FDB_GUARD_BEGIN
   if (!h || !host_slab) return set_error(FDB_E_INVALID, "null argument");
-  return field_download(&h->field, h->field.cur, nullptr, host_slab);
+  return upwind_download(h, nullptr, host_slab);
   FDB_GUARD_END
 }
 

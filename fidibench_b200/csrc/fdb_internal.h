@@ -153,7 +153,10 @@ int field_set_stream(Field* f, void* stream);
 // async: no host synchronisation at all, the copy is ordered behind the handle's earlier work
 int field_upload(Field* f, int p, const double* host_global, const double* host_slab, bool async = false);
 int field_download(Field* f, int p, double* host_global, double* host_slab);
-int field_fill_delta(Field* f, int p);
+int field_fill_delta(Field* f, int p, int64_t cell = 0);  // zero field, global cell `cell` = 1
+// single-slab fields: buf[dst] = buf[src] mirrored along the flagged axes, on the main stream; buf[dst]
+// becomes the current field when `publish`
+int field_mirror(Field* f, int src, int dst, const bool* flip, bool publish);
 // (re)fill the ghosts of buf[p] from the neighbours' boundary planes; enqueued on
 // the boundary streams, ev_ghost_ready[p] recorded.  `after_bnd` = wait for
 // ev_bnd_done (the planes were just produced by a boundary kernel) instead of
@@ -225,6 +228,7 @@ int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode,
 int64_t reduce_partials_per_plane(int64_t plane);
 int launch_fill(double* p, int64_t n, double v, cudaStream_t s);
 int launch_permute(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, cudaStream_t s);
+int launch_mirror(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, const bool* flip, cudaStream_t s);
 
 int encode_tensor_map_3d(CUtensorMap* tm, const double* base, int64_t n2, int64_t n1, int64_t n0,
                          int box2, int box1);

@@ -133,6 +133,21 @@ __global__ void __launch_bounds__(kThreads) permute210_kernel(const double* __re
   }
 }
 
+// out[i][j][k] = in[i'][j'][k'] with each primed index mirrored (n-1-x) where its flag is set: turns a
+// negative velocity along an axis into a positive one on the mirrored grid (capi.cu: upwind flips)
+__global__ void __launch_bounds__(kThreads) mirror_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                          int64_t n0, int64_t n1, int64_t n2, int f0, int f1, int f2) {
+  const int64_t total = n0 * n1 * n2;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * kThreads) {
+    const int64_t k = t % n2;
+    const int64_t j = (t / n2) % n1;
+    const int64_t i = t / (n2 * n1);
+    const int64_t ii = f0 ? n0 - 1 - i : i, jj = f1 ? n1 - 1 - j : j, kk = f2 ? n2 - 1 - k : k;
+    out[t] = in[(ii * n1 + jj) * n2 + kk];
+  }
+}
+
 // ---- reductions ---------------------------------------------------------------
 // Stage 1: block (c, i) reduces chunk c of plane i in a fixed order -> partial.
 // Stage 2: block i reduces its plane's partials in a fixed order -> plane_sums[i].
@@ -270,6 +285,16 @@ int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode,
 int launch_fill(double* p, int64_t n, double v, cudaStream_t s) {
   if (n <= 0) return FDB_OK;
   fill_kernel<<<grid_for(n), kThreads, 0, s>>>(p, n, v);
+  count_launch();
+  FDB_CUDA(cudaGetLastError());
+  return FDB_OK;
+}
+
+int launch_mirror(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, const bool* flip,
+                  cudaStream_t s) {
+  const int64_t total = n0 * n1 * n2;
+  if (total <= 0) return FDB_OK;
+  mirror_kernel<<<grid_for(total), kThreads, 0, s>>>(in, out, n0, n1, n2, flip[0], flip[1], flip[2]);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;

@@ -440,16 +440,25 @@ int field_download(Field* f, int p, double* host_global, double* host_slab) {
 }
 
 // ref: Upwind ctor, upwind.cxx:45-48 -- zero field, cell 0 = 1
-int field_fill_delta(Field* f, int p) {
+int field_fill_delta(Field* f, int p, int64_t cell) {
   FDB_TRY(field_sync(f));
   const int64_t plane = f->geo.plane();
   for (int d = 0; d < f->ngpus; ++d) {
     Slab& s = f->slabs[d];
     FDB_CUDA(cudaSetDevice(s.device));
     FDB_TRY(launch_fill(f->body(d, p), s.nloc() * plane, 0.0, s.s_main));
-    if (s.lo == 0) FDB_TRY(launch_fill(f->body(d, p), 1, 1.0, s.s_main));
+    if (cell >= s.lo * plane && cell < s.hi * plane)
+      FDB_TRY(launch_fill(f->body(d, p) + (cell - s.lo * plane), 1, 1.0, s.s_main));
   }
   return field_publish(f, p);
+}
+
+int field_mirror(Field* f, int src, int dst, const bool* flip, bool publish) {
+  if (!f->single() || src == dst) return set_error(FDB_E_STATE, "mirroring needs a single-slab field and two buffers");
+  Slab& s = f->slabs[0];
+  FDB_CUDA(cudaSetDevice(s.device));
+  FDB_TRY(launch_mirror(f->body(0, src), f->body(0, dst), f->geo.n[0], f->geo.n[1], f->geo.n[2], flip, s.s_main));
+  return publish ? field_publish(f, dst) : FDB_OK;
 }
 
 // Fill the ghosts of buf[p].  Pull model: the copy runs on the RECEIVING device's

@@ -99,11 +99,15 @@ def test_negative_and_zero_velocities(gpu_fb):
         assert np.array_equal(f, C.upwind_advect(a, 6, velocity=vel, lengths=[1, 2, 1], dt=0.004))
 
 
-def test_tma_kernel_rejects_what_it_cannot_run(gpu_fb):
+def test_tma_kernel_rejects_what_it_cannot_run(gpu_fb, monkeypatch):
+    monkeypatch.setenv("FDB_NO_FLIP", "1")  # without axis mirroring a negative velocity needs the generic kernel
     with gpu_fb.Upwind([1.0, -1.0, 1.0], [1.0] * 3, [8, 8, 8]) as up:
         assert up.kernel() == gpu_fb.FDB_KERNEL_GENERIC
         with pytest.raises(gpu_fb.FdbError):
             up.set_kernel(gpu_fb.FDB_KERNEL_TMA)
+    monkeypatch.delenv("FDB_NO_FLIP")
+    with gpu_fb.Upwind([1.0, -1.0, 1.0], [1.0] * 3, [8, 8, 8]) as up:  # mirrored along axis 1 on the device
+        assert up.kernel() == gpu_fb.FDB_KERNEL_TMA
     with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [8, 8, 9]) as up:  # odd rows are not 16-byte pitched
         assert up.kernel() == gpu_fb.FDB_KERNEL_GENERIC
 
@@ -289,3 +293,30 @@ def test_repeated_advect_calls_on_slabs_refresh_deeper_ghosts(gpu_fb, ngpus):
             up.advect(n, dt)
         f = up.field()
     assert np.array_equal(f, C.upwind_advect(a, 21))
+
+
+@pytest.mark.parametrize("vel", [[-1.0, 1.0, 1.0], [1.0, -0.5, 2.0], [1.0, 1.0, -1.0], [-1.0, -2.0, -0.25]])
+@pytest.mark.parametrize("fuse", [1, 3])
+def test_negative_velocities_run_the_tiled_kernels_on_a_mirrored_grid(gpu_fb, vel, fuse):
+    """A negative velocity along an axis is a positive one on the mirrored grid with the same coefficient
+    bits; uploads, downloads and the ctor's delta are mirrored, so the caller never sees it."""
+    rng = np.random.default_rng(SEED + 31)
+    shape, lengths, dt = (16, 24, 64), [1.0, 1.5, 2.0], 0.002
+    a = rng.random(shape)
+    with gpu_fb.Upwind(vel, lengths, shape) as up:
+        assert up.kernel() == gpu_fb.FDB_KERNEL_TMA
+        up.set_fuse(fuse)
+        up.set_field(a)
+        assert np.array_equal(up.field(), a)                      # upload + download round trip
+        up.advect(7, dt)
+        ref = C.upwind_advect(a, 7, velocity=vel, lengths=lengths, dt=dt)
+        assert np.array_equal(up.field(), ref)
+        assert np.array_equal(up.slab(), ref)
+        assert abs(up.checksum() - C.checksum(ref)) <= 1e-12 * abs(C.checksum(ref))
+        assert abs(up.std() - C.std(ref)) <= 1e-12 * C.std(ref)
+        up.advect(2, dt)                                          # carries on from the mirrored state
+        assert np.array_equal(up.field(), C.upwind_advect(a, 9, velocity=vel, lengths=lengths, dt=dt))
+        up.reset()                                                # the delta sits at reference cell 0
+        assert np.array_equal(up.field(), delta(shape))
+        up.advect(5, dt)
+        assert np.array_equal(up.field(), C.upwind_advect(delta(shape), 5, velocity=vel, lengths=lengths, dt=dt))
