@@ -88,7 +88,15 @@ class Filter {
 
   void applyFilter() { check(fdb_stencil_apply(h_)); }  // ref: Filter.cpp:191-263
   void copyOutToIn() { check(fdb_stencil_swap(h_)); }   // ref: Filter.cpp:440-463
+  // niter x { applyFilter(); copyOutToIn(); } (ref: laplacian.cxx:86-90) in one call: the 3-D 7-point stencil
+  // then runs two applies per sweep (same bits); setFuse(1) turns that off, fuse() tells what will run
   void iterate(long niter) { check(fdb_stencil_iterate(h_, niter)); }
+  void setFuse(int appliesPerSweep) { check(fdb_stencil_set_fuse(h_, appliesPerSweep)); }
+  int fuse() const {
+    int n = 1;
+    check(fdb_stencil_get_fuse(h_, &n));
+    return n;
+  }
 
   // ref: Filter.cpp:465-485
   double computeCheckSum(const std::string& inOrOut) {

@@ -63,3 +63,31 @@ def test_cube_decomp_argument_errors(fb):
     assert _lib.lib.fdb_cube_decomp(2, 4, _lib.arr_i64([8, 8, 8, 8]), grid) == _lib.FDB_E_INVALID
     assert _lib.lib.fdb_cube_decomp(3, 3, _lib.arr_i64([8, 8, 8]), grid) == _lib.FDB_E_DECOMP
     assert b"No valid domain decomposition" in _lib.lib.fdb_last_error()
+
+
+def test_cpp_front_has_the_reference_interface(fb, tmp_path):
+    """drivers/CubeDecomp.hpp: build / getDecomp / getBegIndices / getEndIndices / getNeighborRank as
+    cxx/CubeDecomp.h declares them, answering like the reference (fixture row: 16 ranks on 128^3)."""
+    import subprocess
+    from conftest import ROOT
+    src = tmp_path / "cd.cxx"
+    src.write_text(r'''
+#include <iostream>
+#include "CubeDecomp.hpp"
+int main() {
+  fidib200::CubeDecomp d;
+  std::vector<size_t> dims(3, 128);
+  if (!d.build(16, dims)) return 1;
+  std::vector<size_t> g = d.getDecomp(), b = d.getBegIndices(5), e = d.getEndIndices(5);
+  std::vector<int> dir(3, 0); dir[0] = 1;
+  std::cout << g[0] << ' ' << g[1] << ' ' << g[2] << ' ' << b[0] << ' ' << b[1] << ' ' << b[2] << ' '
+            << e[0] << ' ' << e[1] << ' ' << e[2] << ' ' << d.getNeighborRank(5, dir) << ' ' << d.build(3, dims) << '\n';
+}''')
+    exe = tmp_path / "cd"
+    lib = os.path.join(ROOT, "fidibench_b200", "lib")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "drivers"),
+                    str(src), "-o", str(exe), "-L", lib, "-lfidib200", f"-Wl,-rpath,{lib}", "-Wl,--allow-shlib-undefined"],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["4", "2", "2", "32", "0", "64", "64", "64", "128", "9", "0"]
