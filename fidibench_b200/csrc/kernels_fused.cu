@@ -335,10 +335,10 @@ constexpr FusedConfig make_fused(const char* name) {
 }
 // per T: index 0 is the default, the rest are tuning alternatives (env FDB_FUSED_CFG)
 const FusedConfig kFused2[] = {
-    make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),
-    make_fused<FusedCfg<2, 18, 6, 4>>("t2_cj18_r6_s4"),
-    make_fused<FusedCfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),
-    make_fused<FusedCfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),
+    make_fused<FusedCfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),  // 760 GCUPS at 512^3 (profiles/r01n_*)
+    make_fused<FusedCfg<2, 18, 6, 4>>("t2_cj18_r6_s4"),  // 630
+    make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),  // 673
+    make_fused<FusedCfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),  // 629
 };
 const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // 835 / 867 GCUPS at 512^3 / 1024^3 (profiles/r01l_*)

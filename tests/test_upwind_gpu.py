@@ -238,16 +238,22 @@ def test_fused_config1_golden(gpu_fb):
             assert up.checksum() == pytest.approx(float(g["checksum"]), rel=RTOL)
 
 
-def test_fuse_argument_validation(gpu_fb):
+def test_fuse_argument_validation(gpu_fb, monkeypatch):
     with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [16, 16, 16]) as up:
         with pytest.raises(gpu_fb.FdbError):
             up.set_fuse(-1)
         with pytest.raises(gpu_fb.FdbError):
             up.set_fuse(9)
         up.set_fuse(0)  # auto
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, [16, 16, 15]) as up:
+        with pytest.raises(gpu_fb.FdbError):
+            up.set_fuse(2)  # odd last extent: no TMA path, no fused path
+    with gpu_fb.Upwind([1.0, -1.0, 1.0], [1.0] * 3, [16, 16, 16]) as up:
+        up.set_fuse(2)      # negative velocity: mirrored on the device, the fused kernel runs
+    monkeypatch.setenv("FDB_NO_FLIP", "1")
     with gpu_fb.Upwind([1.0, -1.0, 1.0], [1.0] * 3, [16, 16, 16]) as up:
         with pytest.raises(gpu_fb.FdbError):
-            up.set_fuse(2)  # negative velocity: no TMA path, no fused path
+            up.set_fuse(2)  # ... unless mirroring is switched off: generic kernel only
 
 
 @pytest.mark.parametrize("ngpus", [2, 4])
