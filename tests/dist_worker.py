@@ -61,6 +61,71 @@ def host_model_of_the_slab_ring(rank, world):
     assert np.array_equal(cur, ref[lo:hi]), "host slab-ring model differs from the single-domain result"
 
 
+def host_model_of_the_two_sided_ring_with_fused_pairs(rank, world):
+    """The stencil engine's multi-slab protocol (runtime.cu: field_run_sweeps / sweep_device_direct, capi.cu:
+    fdb_stencil_iterate) restated with numpy slabs and gloo send/recv: G = 2 ghost planes on both sides, a plan of
+    sweeps that do two applies each (reading two ghost planes, refreshing two) and an odd apply at the end (one
+    plane), the depth of the last exchange tracked, and a full-depth refresh when the next plan starts deeper than
+    the ghosts it finds.  Must equal the single-domain 7-point applies bit for bit."""
+    G = 2
+    n0, n1, n2 = 6 * world, 5, 8
+    rng = np.random.default_rng(SEED + 7)
+    full = rng.random((n0, n1, n2))
+    w = [1.0, 1.0, 1.0, -6.0, 1.0, 1.0, 1.0]        # std::map order of the offsets (Filter.cpp:202)
+    lo, hi = fb.slab_partition(n0, world, rank)
+    nloc = hi - lo
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+
+    def apply(ext):
+        """one apply on every plane of `ext` that has both neighbours: returns ext[1:-1] applied"""
+        c, below, above = ext[1:-1], ext[:-2], ext[2:]
+        acc = 0.0 + w[0] * below
+        acc = acc + w[1] * np.roll(c, 1, axis=1)
+        acc = acc + w[2] * np.roll(c, 1, axis=2)
+        acc = acc + w[3] * c
+        acc = acc + w[4] * np.roll(c, -1, axis=2)
+        acc = acc + w[5] * np.roll(c, -1, axis=1)
+        acc = acc + w[6] * above
+        return acc
+
+    def exchange(body, depth):
+        """push `depth` boundary planes to both neighbours; returns (ghost_lo, ghost_hi), nearest planes valid"""
+        reqs = [dist.isend(torch.from_numpy(body[-depth:].copy()), nxt),   # my top planes -> next's ghosts below
+                dist.isend(torch.from_numpy(body[:depth].copy()), prv)]    # my bottom planes -> prev's ghosts above
+        glo_t = torch.empty((depth, n1, n2), dtype=torch.float64)
+        ghi_t = torch.empty((depth, n1, n2), dtype=torch.float64)
+        reqs += [dist.irecv(glo_t, prv), dist.irecv(ghi_t, nxt)]
+        for r in reqs:
+            r.wait()
+        glo = np.full((G, n1, n2), np.nan); ghi = np.full((G, n1, n2), np.nan)   # planes beyond `depth` are stale
+        glo[G - depth:] = glo_t.numpy(); ghi[:depth] = ghi_t.numpy()
+        return glo, ghi
+
+    body = full[lo:hi].copy()
+    glo, ghi = exchange(body, G)        # publish after the upload: full depth
+    ghost_depth = G
+    applied = 0
+    for plan in ([2, 2, 1], [2, 2], [1], [2, 1]):
+        assert all(a >= b for a, b in zip(plan, plan[1:])), "a plan never deepens"
+        if plan[0] > ghost_depth:       # the previous plan ended on a one-plane exchange
+            glo, ghi = exchange(body, G)
+            ghost_depth = G
+        for depth in plan:
+            ext = np.concatenate([glo[G - depth:], body, ghi[:depth]])
+            assert not np.isnan(ext).any(), "sweep read a stale ghost plane"
+            for _ in range(depth):
+                ext = apply(ext)        # each apply eats one plane on both ends
+            assert ext.shape[0] == nloc
+            body = ext
+            glo, ghi = exchange(body, depth)
+            ghost_depth = depth
+            applied += depth
+    ref = full.copy()
+    for _ in range(applied):
+        ref = apply(np.concatenate([ref[-1:], ref, ref[:1]]))
+    assert np.array_equal(body, ref[lo:hi]), "two-sided slab ring differs from the single-domain applies"
+
+
 def cpu_main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -84,6 +149,7 @@ def cpu_main():
     assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
     # 4. the halo protocol itself
     host_model_of_the_slab_ring(rank, world)
+    host_model_of_the_two_sided_ring_with_fused_pairs(rank, world)
     dist.barrier()
     print(f"RANK {rank} OK cpu", flush=True)
     dist.destroy_process_group()
