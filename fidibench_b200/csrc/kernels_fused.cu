@@ -45,13 +45,9 @@ using namespace ptx;
 
 constexpr int fz_align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int T_, int CJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1, bool SKEW_ = false>
+template <int T_, int CJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1>
 struct FusedCfg {
   static constexpr int T = T_, CJ = CJ_, R = R_, STAGES = STAGES_, BK = BK_, MINB = MINB_;
-  // SKEW: level s+1 is computed one plane-step after level s (from registers and the exchange tiles of the
-  // previous step), so the T level updates of a step are independent of one another and ONE barrier per
-  // plane-step serves all levels -- at the price of T-1 extra steps per work item and T-1 more kept planes
-  static constexpr bool SKEW = SKEW_;
   static constexpr int HKC = 2 * (T / 2);          // redundant compute columns on the left (even, >= T-1)
   static constexpr int CK = BK + HKC;              // compute columns: global k0-HKC .. k0+BK-1
   static constexpr int TX = CK / 2;                // threads per row (2 cells each)
@@ -74,7 +70,7 @@ struct FusedCfg {
   static constexpr int TX_MAIN = IN_ROWS * PITCH;
   static constexpr int TX_WRAP = IN_ROWS * WPITCH;
   static constexpr int X_BYTES = fz_align128((CJ + 1) * PITCH);  // exchange tile: compute row q at row q + 1
-  static constexpr int NX = SKEW ? 2 * (T - 1) : ((T > 1) ? 2 : 0);  // exchange tiles: per level and parity when skewed
+  static constexpr int NX = (T > 1) ? 2 : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NX * X_BYTES + 3 * STAGES * 8 + 128;
   static constexpr int LAG = STAGES - 2;
   static_assert(CJ % R == 0 && T >= 2 && T <= 4 && HKC >= T - 1 && CJ > T, "bad fused tile");
@@ -265,150 +261,60 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 #pragma unroll
       for (int r = 0; r < C::R; ++r) carry[s][r] = make_double2(0.0, 0.0);
 
-    if constexpr (C::SKEW) {
-      // keep[s]: this thread's cells of level s of plane p-s (made one step ago); carry[s]: of plane p-s-1
-      double2 keep[C::T][C::R];
+    for (int64_t p = i0 - C::T; p < i1; ++p) {
+      ooff += plane;
+      mbar_wait(full + 8 * stage, phase);
+      mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
+      const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
+      double2 v[C::R];
+      double km[C::R];
+      double2 up = lds_v2(sb);
 #pragma unroll
-      for (int s = 0; s < C::T; ++s)
-#pragma unroll
-        for (int r = 0; r < C::R; ++r) keep[s][r] = make_double2(0.0, 0.0);
-      ooff -= (int64_t)(C::T - 1) * plane;  // the stored plane trails the loaded one by T-1
-      for (int64_t p = i0 - C::T; p < i1 + C::T - 1; ++p) {
-        ooff += plane;
-        const uint32_t xr = xbuf + (xsel ^ 1) * C::X_BYTES + xt;  // tiles written one step ago
-        const uint32_t xw = xbuf + xsel * C::X_BYTES + xt;        // tiles written now
-        xsel ^= 1;
-        // levels T-1 .. 1 first: each reads keep[s] before the level below overwrites it
-#pragma unroll
-        for (int s = C::T - 1; s >= 1; --s) {
-          const uint32_t xrs = xr + (s - 1) * 2 * C::X_BYTES;
-          const double2 up = lds_v2(xrs);
-          double2 nv[C::R];
-#pragma unroll
-          for (int r = 0; r < C::R; ++r) {
-            const double km = lds_f64(xrs + (1 + r) * P - 8);
-            const double2 jm = (r == 0) ? up : keep[s][r - 1];
-            nv[r].x = upwind_cell(keep[s][r].x, carry[s][r].x, jm.x, km, c0, c1, c2);
-            nv[r].y = upwind_cell(keep[s][r].y, carry[s][r].y, jm.y, keep[s][r].x, c0, c1, c2);
-          }
-#pragma unroll
-          for (int r = 0; r < C::R; ++r) carry[s][r] = keep[s][r];
-          if (s == C::T - 1) {
-            if (p - (C::T - 1) >= i0 && store_cols) {
-              double* orow = a.out + ooff;
-              const bool push = (a.peer_out != nullptr) && (p - (C::T - 1) >= a.peer_from);
-              double* prow = a.peer_out + (ooff - a.peer_from * plane);
-#pragma unroll
-              for (int r = 0; r < C::R; ++r) {
-                if ((rmask >> r) & 1u) {
-                  st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
-                  if (push) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
-                }
-              }
-            }
-          } else {
-            const uint32_t xws = xw + s * 2 * C::X_BYTES;  // level s+1
-            if (worker) {
-#pragma unroll
-              for (int r = 0; r < C::R; ++r) sts_v2(xws + (1 + r) * P, nv[r].x, nv[r].y);
-            }
-#pragma unroll
-            for (int r = 0; r < C::R; ++r) keep[s + 1][r] = nv[r];
-          }
-        }
-        // level 0 -> 1 from the stage (no more planes to load in the last T-1 steps)
-        if (p < i1) {
-          mbar_wait(full + 8 * stage, phase);
-          mbar_wait(landed + 8 * stage, phase);
-          const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
-          double2 v[C::R];
-          double km[C::R];
-          const double2 up = lds_v2(sb);
-#pragma unroll
-          for (int r = 0; r < C::R; ++r) {
-            v[r] = lds_v2(sb + (1 + r) * P);
-            km[r] = lds_f64(sb + (1 + r) * P - 8);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty + 8 * stage);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-          double2 nv[C::R];
-#pragma unroll
-          for (int r = 0; r < C::R; ++r) {
-            const double2 jm = (r == 0) ? up : v[r - 1];
-            nv[r].x = upwind_cell(v[r].x, carry[0][r].x, jm.x, km[r], c0, c1, c2);
-            nv[r].y = upwind_cell(v[r].y, carry[0][r].y, jm.y, v[r].x, c0, c1, c2);
-            carry[0][r] = v[r];
-          }
-          if (C::T == 1) {
-            // (not instantiated: T >= 2)
-          } else {
-            if (worker) {
-#pragma unroll
-              for (int r = 0; r < C::R; ++r) sts_v2(xw + (1 + r) * P, nv[r].x, nv[r].y);  // level 1
-            }
-#pragma unroll
-            for (int r = 0; r < C::R; ++r) keep[1][r] = nv[r];
-          }
-        }
-        named_bar_sync(1, C::CONSUMERS);
+      for (int r = 0; r < C::R; ++r) {
+        v[r] = lds_v2(sb + (1 + r) * P);
+        km[r] = lds_f64(sb + (1 + r) * P - 8);
       }
-    } else {
-      for (int64_t p = i0 - C::T; p < i1; ++p) {
-        ooff += plane;
-        mbar_wait(full + 8 * stage, phase);
-        mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
-        const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
-        double2 v[C::R];
-        double km[C::R];
-        double2 up = lds_v2(sb);
-  #pragma unroll
-        for (int r = 0; r < C::R; ++r) {
-          v[r] = lds_v2(sb + (1 + r) * P);
-          km[r] = lds_f64(sb + (1 + r) * P - 8);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + 8 * stage);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 8 * stage);
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
 
-  #pragma unroll
-        for (int s = 0; s < C::T; ++s) {
-          double2 nv[C::R];
-  #pragma unroll
-          for (int r = 0; r < C::R; ++r) {
-            const double2 jm = (r == 0) ? up : v[r - 1];
-            nv[r].x = upwind_cell(v[r].x, carry[s][r].x, jm.x, km[r], c0, c1, c2);
-            nv[r].y = upwind_cell(v[r].y, carry[s][r].y, jm.y, v[r].x, c0, c1, c2);
-            carry[s][r] = v[r];
-          }
-          if (s == C::T - 1) {
-            if (p >= i0 && store_cols) {
-              double* orow = a.out + ooff;
-              const bool push = (a.peer_out != nullptr) && (p >= a.peer_from);
-              double* prow = a.peer_out + (ooff - a.peer_from * plane);
-  #pragma unroll
-              for (int r = 0; r < C::R; ++r) {
-                if ((rmask >> r) & 1u) {
-                  st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
-                  if (push) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
-                }
+#pragma unroll
+      for (int s = 0; s < C::T; ++s) {
+        double2 nv[C::R];
+#pragma unroll
+        for (int r = 0; r < C::R; ++r) {
+          const double2 jm = (r == 0) ? up : v[r - 1];
+          nv[r].x = upwind_cell(v[r].x, carry[s][r].x, jm.x, km[r], c0, c1, c2);
+          nv[r].y = upwind_cell(v[r].y, carry[s][r].y, jm.y, v[r].x, c0, c1, c2);
+          carry[s][r] = v[r];
+        }
+        if (s == C::T - 1) {
+          if (p >= i0 && store_cols) {
+            double* orow = a.out + ooff;
+            const bool push = (a.peer_out != nullptr) && (p >= a.peer_from);
+            double* prow = a.peer_out + (ooff - a.peer_from * plane);
+#pragma unroll
+            for (int r = 0; r < C::R; ++r) {
+              if ((rmask >> r) & 1u) {
+                st_global_v2(orow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
+                if (push) st_global_v2(prow + (int64_t)r * a.n2, nv[r].x, nv[r].y);
               }
             }
-          } else {
-            // hand level s+1 of this plane to the neighbours through the exchange tile
-            const uint32_t xb = xbuf + xsel * C::X_BYTES + xt;
-            xsel ^= 1;
-            if (worker) {
-  #pragma unroll
-              for (int r = 0; r < C::R; ++r) sts_v2(xb + (1 + r) * P, nv[r].x, nv[r].y);
-            }
-            named_bar_sync(1, C::CONSUMERS);
-            up = lds_v2(xb);
-  #pragma unroll
-            for (int r = 0; r < C::R; ++r) {
-              km[r] = lds_f64(xb + (1 + r) * P - 8);
-              v[r] = nv[r];
-            }
+          }
+        } else {
+          // hand level s+1 of this plane to the neighbours through the exchange tile
+          const uint32_t xb = xbuf + xsel * C::X_BYTES + xt;
+          xsel ^= 1;
+          if (worker) {
+#pragma unroll
+            for (int r = 0; r < C::R; ++r) sts_v2(xb + (1 + r) * P, nv[r].x, nv[r].y);
+          }
+          named_bar_sync(1, C::CONSUMERS);
+          up = lds_v2(xb);
+#pragma unroll
+          for (int r = 0; r < C::R; ++r) {
+            km[r] = lds_f64(xb + (1 + r) * P - 8);
+            v[r] = nv[r];
           }
         }
       }
@@ -434,7 +340,6 @@ const FusedConfig kFused2[] = {
     make_fused<FusedCfg<2, 18, 6, 4>>("t2_cj18_r6_s4"),  // 630
     make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),  // 673
     make_fused<FusedCfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),  // 629
-    make_fused<FusedCfg<2, 21, 3, 4, 128, 1, true>>("t2_cj21_r3_s4_skew"),
 };
 const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // 835 / 867 GCUPS at 512^3 / 1024^3 (profiles/r01l_*)
@@ -445,18 +350,12 @@ const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 21, 3, 6>>("t3_cj21_r3_s6"),
     make_fused<FusedCfg<3, 20, 5, 6>>("t3_cj20_r5_s6"),
     make_fused<FusedCfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
-    // skewed levels, one barrier per plane-step (compiled and pinned by the host model; not yet timed on a B200)
-    make_fused<FusedCfg<3, 21, 3, 4, 128, 1, true>>("t3_cj21_r3_s4_skew"),
-    make_fused<FusedCfg<3, 21, 3, 3, 128, 1, true>>("t3_cj21_r3_s3_skew"),
-    make_fused<FusedCfg<3, 18, 3, 4, 128, 1, true>>("t3_cj18_r3_s4_skew"),
-    make_fused<FusedCfg<3, 18, 6, 4, 128, 1, true>>("t3_cj18_r6_s4_skew"),
 };
 const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
     make_fused<FusedCfg<4, 18, 3, 4>>("t4_cj18_r3_s4"),
     make_fused<FusedCfg<4, 18, 6, 6>>("t4_cj18_r6_s6"),
     make_fused<FusedCfg<4, 20, 4, 6>>("t4_cj20_r4_s6"),
-    make_fused<FusedCfg<4, 21, 3, 3, 128, 1, true>>("t4_cj21_r3_s3_skew"),
 };
 
 const FusedConfig* fz_table(int T, int* count) {

@@ -35,7 +35,7 @@ class Cfg:
 
 
 def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, ibeg: int, iend: int,
-                out: np.ndarray, skew: bool = False) -> None:
+                out: np.ndarray) -> None:
     """One launch on the slab [lo,hi) of the periodic field x: local output planes [ibeg,iend) of `out`
     receive the field T time steps later.  c = (c0, c1, c2)."""
     C = cfg
@@ -71,24 +71,8 @@ def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, i
         return mem[addr // 8]
 
     smem = np.full(C.STAGE_BYTES // 8, np.nan)
-    nx = 2 * (T - 1) if skew else 2
-    xbuf = [np.full(C.X_BYTES // 8, np.nan) for _ in range(nx)]
+    xbuf = [np.full(C.X_BYTES // 8, np.nan), np.full(C.X_BYTES // 8, np.nan)]
     xsel = 0
-
-    def load_stage(p, kb, jh, j0, first_k):
-        """the loader warp: TMA boxes of plane p, then the wrap columns copied into the tile rows"""
-        smem[:] = np.nan
-        t, pl = (glo, G + p) if p < 0 else (body, p)
-        tma_box(smem, 0, t, kb, jh, pl, C.BKP, C.HR)
-        tma_box(smem, C.BODY_OFF, t, kb, j0, pl, C.BKP, C.BJ)
-        if first_k:
-            tma_box(smem, C.W_OFF, t, n2 - 8, jh, pl, 8, C.HR)
-            tma_box(smem, C.W_OFF + C.HR * C.WPITCH, t, n2 - 8, j0, pl, 8, C.BJ)
-            lanes = np.arange(C.IN_ROWS)
-            for off in (16, 32, 48):
-                vv = lds_v2(smem, C.W_OFF + lanes * C.WPITCH + off)
-                ad = (lanes * C.PITCH + off) // 8
-                smem[ad], smem[ad + 1] = vv[:, 0], vv[:, 1]
     planes = iend - ibeg
     nchunk = (planes + ci - 1) // ci
     for wi in range(njt * nkt * nchunk):
@@ -106,59 +90,6 @@ def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, i
         store_cols = (2 * tx >= C.HKC) & (k < n2)
         rmask = [rowmask[r] & (j + r < n1) for r in range(C.R)]
         carry = np.zeros((T, C.R, C.WORKERS, 2))
-        if skew:
-            # levels T-1 .. 1 work on what the previous step left in registers (keep) and in the exchange
-            # tiles; level 0 -> 1 on the stage; ONE barrier per step
-            keep = np.zeros((T, C.R, C.WORKERS, 2))
-            for p in range(i0 - T, i1 + T - 1):
-                xr, xw = xsel ^ 1, xsel
-                xsel ^= 1
-                for s_ in range(T - 1, 0, -1):
-                    xt_r = xbuf[(s_ - 1) * 2 + xr]
-                    up = lds_v2(xt_r, xt)
-                    nv = np.empty((C.R, C.WORKERS, 2))
-                    for r in range(C.R):
-                        kmv = lds_f64(xt_r, xt + (1 + r) * P - 8)
-                        jm = up if r == 0 else keep[s_, r - 1]
-                        nv[r, :, 0] = cell(keep[s_, r, :, 0], carry[s_, r, :, 0], jm[:, 0], kmv)
-                        nv[r, :, 1] = cell(keep[s_, r, :, 1], carry[s_, r, :, 1], jm[:, 1], keep[s_, r, :, 0])
-                    carry[s_] = keep[s_]
-                    if s_ == T - 1:
-                        q = p - (T - 1)
-                        if q >= i0:
-                            for r in range(C.R):
-                                ok = store_cols & rmask[r]
-                                rows, cols = (j + r)[ok], k[ok]
-                                assert q < i1 and np.all(np.isnan(out[q, rows, cols])), "cell stored twice"
-                                out[q, rows, cols] = nv[r, ok, 0]
-                                out[q, rows, cols + 1] = nv[r, ok, 1]
-                    else:
-                        xt_w = xbuf[s_ * 2 + xw]
-                        xt_w[:] = np.nan
-                        for r in range(C.R):
-                            ad = (xt + (1 + r) * P) // 8
-                            xt_w[ad], xt_w[ad + 1] = nv[r, :, 0], nv[r, :, 1]
-                        keep[s_ + 1] = nv
-                if p < i1:
-                    load_stage(p, kb, jh, j0, first_k)
-                    up = lds_v2(smem, tb)
-                    v = np.empty((C.R, C.WORKERS, 2))
-                    nv = np.empty((C.R, C.WORKERS, 2))
-                    for r in range(C.R):
-                        v[r] = lds_v2(smem, tb + (1 + r) * P)
-                    for r in range(C.R):
-                        kmv = lds_f64(smem, tb + (1 + r) * P - 8)
-                        jm = up if r == 0 else v[r - 1]
-                        nv[r, :, 0] = cell(v[r, :, 0], carry[0, r, :, 0], jm[:, 0], kmv)
-                        nv[r, :, 1] = cell(v[r, :, 1], carry[0, r, :, 1], jm[:, 1], v[r, :, 0])
-                    carry[0] = v
-                    xt_w = xbuf[xw]
-                    xt_w[:] = np.nan
-                    for r in range(C.R):
-                        ad = (xt + (1 + r) * P) // 8
-                        xt_w[ad], xt_w[ad + 1] = nv[r, :, 0], nv[r, :, 1]
-                    keep[1] = nv
-            continue
         for p in range(i0 - T, i1):
             # ---- loader
             smem[:] = np.nan

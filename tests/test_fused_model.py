@@ -31,23 +31,6 @@ def test_model_single_slab(T, CJ, R, BK, shape, ci):
     assert np.array_equal(out, oracle.c.upwind_advect(x, T))
 
 
-@pytest.mark.parametrize("T,CJ,R,shape,ci", [
-    (3, 21, 3, (6, 40, 260), 4),     # ragged tiles on both axes, ragged chunks
-    (3, 18, 6, (4, 16, 128), 8),
-    (2, 21, 3, (3, 24, 136), 2),
-    (4, 21, 3, (5, 20, 132), 5),
-])
-def test_model_skewed_levels(T, CJ, R, shape, ci):
-    """The skewed variant (one barrier per plane-step, levels one step apart) computes the same bits."""
-    rng = np.random.default_rng(SEED + 3)
-    x = rng.random(shape)
-    out = np.full(shape, np.nan)
-    dt = oracle.c.upwind_dt(shape, [1.0] * 3, [1.0] * 3)
-    c = [((dt * 1.0) * -1) / (1.0 / shape[j]) for j in range(3)]
-    fused_steps(x, c, 0, shape[0], T, Cfg(T, CJ, R), ci, 0, shape[0], out, skew=True)
-    assert np.array_equal(out, oracle.c.upwind_advect(x, T))
-
-
 def test_model_slab_of_a_ring():
     """Slab [4,8) of 12 planes, ghost depth 4 (the upwind engine's), launched as the runtime does: top
     planes first, then the rest; anisotropic coefficients."""
