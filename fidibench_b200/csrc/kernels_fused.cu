@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
           sts_v2(st + lane * C::PITCH + 32, v1.x, v1.y);
           sts_v2(st + lane * C::PITCH + 48, v2.x, v2.y);
         }
+        fence_proxy_async_shared();  // the patched cells are rewritten by a later TMA box
         __syncwarp();
         if (lane == 0) mbar_arrive(full + 8 * sf);
         cf.next(a);

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
             sts_v2(st + lane * C::PITCH + C::CK * 8, v.x, v.y);
           }
         }
+        fence_proxy_async_shared();  // the patched cells are rewritten by a later TMA box
         __syncwarp();
         if (lane == 0) mbar_arrive(full + 8 * sf);
         cf.next(a);
