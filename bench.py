@@ -126,6 +126,10 @@ def reference_arm(args, rank, world):
     bounded sample of the same workload."""
     if rank != 0:
         return 0
+    # the reference's own run-time recipe (scripts/fdi_maui_vs_mahuika.py:9): threads pinned to cores.  Must be in
+    # the environment before libgomp initialises, i.e. before the reference library is loaded.
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ.setdefault("OMP_PLACES", "cores")
     import numpy as np
     import oracle
     dims, scaling = workload_dims(args.workload, args.gpus)
@@ -149,7 +153,7 @@ def reference_arm(args, rank, world):
             t0 = time.perf_counter(); oracle.c.upwind_advect(f0, t); return time.perf_counter() - t0
         kind = "port"
     t1 = run(1)  # calibration (also first-touch)
-    budget = 150.0
+    budget = args.budget
     tsteps = int(max(1, min(args.tsteps, budget / max(t1, 1e-3) / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
         run(tsteps)
@@ -157,7 +161,8 @@ def reference_arm(args, rank, world):
     for _ in range(args.steps):
         secs += run(tsteps)
     value = cells * tsteps * args.steps / secs / 1e9
-    sample = f"{sdims[0]}x{sdims[1]}x{sdims[2]} grid, {tsteps} time step(s) per bench step, advect() only"
+    sample = (f"{sdims[0]}x{sdims[1]}x{sdims[2]} grid, {tsteps} time step(s) per bench step, advect() only, "
+              f"{'untouched upwind.cxx -O3 -fopenmp, OMP_PROC_BIND=' + os.environ.get('OMP_PROC_BIND', '') if use_ref else 'oracle/fdb_oracle.c'}")
     line = {
         "impl": "reference", "metric": "GCUPS (FP64 cell-updates/s), upwind 3-D", "value": value, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
@@ -172,29 +177,18 @@ def reference_arm(args, rank, world):
     return 0
 
 
-def cpu_baseline(sdims, tsteps_hint=10):
-    """oracle/_ref (the untouched reference, OpenMP on every host core) timed on a bounded
-    sample; reported beside the GPU number, not a target."""
-    import numpy as np
-    import oracle
-    ncpu = os.cpu_count() or 1
-    cells = float(np.prod(sdims))
-    if oracle.ref_available():
-        r = oracle.ref()
-        r.set_threads(ncpu)
-        threads, kind = r.threads(), "reference"
-        run = lambda t: r.upwind_run(sdims, t, want_field=False)["seconds"]
-    else:
-        threads, kind = oracle.c.num_threads(), "port"
-        f0 = np.zeros(sdims); f0.reshape(-1)[0] = 1.0
-        def run(t):
-            t0 = time.perf_counter(); oracle.c.upwind_advect(f0, t); return time.perf_counter() - t0
-    t1 = run(1)
-    tsteps = int(max(1, min(tsteps_hint, 15.0 / max(t1, 1e-3))))
-    secs = run(tsteps)
-    return {"value": cells * tsteps / secs / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
-            "sample": f"{sdims[0]}x{sdims[1]}x{sdims[2]} x {tsteps} time steps, advect() only, "
-                      f"{'untouched upwind.cxx -O3 -fopenmp' if kind == 'reference' else 'oracle/fdb_oracle.c'}"}
+def cpu_baseline(workload, tsteps_hint=10):
+    """The reference arm (the untouched upwind.cxx, OpenMP on every host core, threads pinned as the reference's
+    scripts do) run once in a process of its own on a bounded sample; reported beside the GPU number, not a target.
+    A separate process because OMP_PROC_BIND has to be set before libgomp starts and must not pin this one."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--workload", workload, "--tsteps", str(tsteps_hint), "--budget", "15"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    if p.returncode != 0 or not lines:
+        raise RuntimeError("reference arm failed: " + p.stderr[-500:])
+    return json.loads(lines[-1])["cpu_baseline"]
 
 
 def lap_cpu_baseline(niter_hint=2):
@@ -394,6 +388,8 @@ def main():
     ap.add_argument("--tsteps", type=int, default=100, help="time steps per advect() call (= per bench step)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tma"])
     ap.add_argument("--fuse", type=int, default=0, help="time steps per sweep (temporal blocking), 0 = library default")
+    ap.add_argument("--budget", type=float, default=150.0,
+                    help="reference arm: seconds of host work the whole run may take (bounds the time steps per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -555,7 +551,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline((512, 512, 512) if dims[0] >= 512 else dims)
+        cpu = cpu_baseline(args.workload)
 
     if rank == 0:
         line = {
