@@ -41,9 +41,13 @@ constexpr int lf_align128(int x) { return (x + 127) / 128 * 128; }
 
 // UNIT: the six off-centre weights are exactly 1.0 (the Laplacian, laplacian.cxx:55-65): their
 // multiplies are skipped, which is exact (1.0 * v == v for every v), so the bits do not change.
-template <int BJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1>
+template <int BJ_, int R_, int STAGES_, int BK_ = 128, int MINB_ = 1, bool SHFL_ = false>
 struct LapFusedCfg {
   static constexpr int BJ = BJ_, BK = BK_, R = R_, STAGES = STAGES_, MINB = MINB_;
+  // SHFL (experimental, not the default): the k-1 / k+1 neighbours come from the adjacent lanes' registers by
+  // warp shuffle instead of 64-bit shared-memory loads at a 16-byte stride (4 wavefronts each, 60 % of the
+  // kernel's shared-memory wavefronts, profiles/r01k_*); only a warp's edge lanes and a row's end threads load
+  static constexpr bool SHFL = SHFL_;
   static constexpr int CJ = BJ + 2;       // level-1 rows:    global j0-1 .. j0+BJ
   static constexpr int CK = BK + 4;       // level-1 columns: global k0-2 .. k0+BK+1
   static constexpr int IN_ROWS = BJ + 4;  // level-0 rows:    global j0-2 .. j0+BJ+1 (stage row s)
@@ -248,6 +252,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   for (int r = 0; r < C::R; ++r)
     if (q0 + r >= 1 && q0 + r <= C::CJ - 2) rowmask |= 1u << r;
   const bool store_cols = worker && tx >= 1 && tx <= C::TX - 2;
+  // SHFL: lanes whose left / right neighbour cell is not in the adjacent lane (warp edge, row end, and the
+  // last worker, whose next lane is a padding thread)
+  const bool edge_lo = lane == 0 || tx == 0;
+  const bool edge_hi = lane == 31 || tx == C::TX - 1 || tid >= C::WORKERS - 1;
   const int64_t plane = a.n1 * a.n2;
 
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
@@ -282,8 +290,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 #pragma unroll
       for (int r = 0; r < C::R; ++r) {
         c[r] = lds_v2(sb + (1 + r) * P);
-        km[r] = lds_f64(sb + (1 + r) * P - 8);
-        kp[r] = lds_f64(sb + (1 + r) * P + 16);
+        if (C::SHFL) {
+          km[r] = __shfl_up_sync(0xffffffffu, c[r].y, 1);
+          kp[r] = __shfl_down_sync(0xffffffffu, c[r].x, 1);
+          if (edge_lo) km[r] = lds_f64(sb + (1 + r) * P - 8);
+          if (edge_hi) kp[r] = lds_f64(sb + (1 + r) * P + 16);
+        } else {
+          km[r] = lds_f64(sb + (1 + r) * P - 8);
+          kp[r] = lds_f64(sb + (1 + r) * P + 16);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + 8 * stage);
@@ -336,8 +351,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
         const double2 dn1 = lds_v2(xb + (C::R + 1) * P);
 #pragma unroll
         for (int r = 0; r < C::R; ++r) {
-          km[r] = lds_f64(xb + (1 + r) * P - 8);
-          kp[r] = lds_f64(xb + (1 + r) * P + 16);
+          if (C::SHFL) {
+            km[r] = __shfl_up_sync(0xffffffffu, l1[r].y, 1);
+            kp[r] = __shfl_down_sync(0xffffffffu, l1[r].x, 1);
+            if (edge_lo) km[r] = lds_f64(xb + (1 + r) * P - 8);
+            if (edge_hi) kp[r] = lds_f64(xb + (1 + r) * P + 16);
+          } else {
+            km[r] = lds_f64(xb + (1 + r) * P - 8);
+            kp[r] = lds_f64(xb + (1 + r) * P + 16);
+          }
         }
 #pragma unroll
         for (int r = 0; r < C::R; ++r) {
@@ -386,6 +408,9 @@ const LapFusedConfig kLapFused[] = {
     make_lapf<LapFusedCfg<16, 3, 6, 64, 2>>("bj16_r3_s6_bk64_2cta"),
     make_lapf<LapFusedCfg<16, 2, 4, 64, 2>>("bj16_r2_s4_bk64_2cta"),
     make_lapf<LapFusedCfg<8, 5, 6>>("bj8_r5_s6"),
+    // experimental (compiled, pinned by the host model, not yet timed on a B200): shuffled k-neighbours
+    make_lapf<LapFusedCfg<16, 6, 6, 128, 1, true>>("bj16_r6_s6_shfl"),
+    make_lapf<LapFusedCfg<16, 3, 4, 128, 1, true>>("bj16_r3_s4_shfl"),
 };
 constexpr int kNumLapFused = sizeof(kLapFused) / sizeof(kLapFused[0]);
 constexpr int kDefaultLapFused = 7;  // bj16_r6_s6

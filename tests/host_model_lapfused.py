@@ -59,7 +59,7 @@ def tma_box(smem: np.ndarray, dst: int, tensor: np.ndarray, c0: int, c1: int, c2
 
 
 def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: int, ibeg: int, iend: int,
-                      out: np.ndarray, unit: bool = False) -> None:
+                      out: np.ndarray, unit: bool = False, shfl: bool = False) -> None:
     """One launch of the kernel on the slab [lo,hi) of the periodic field x: writes local output
     planes [ibeg,iend) of `out` (shape of the slab).  Ghost tensors hold G planes each."""
     C = cfg
@@ -81,6 +81,19 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
     P = C.PITCH
     rowmask = [(q0 + r >= 1) & (q0 + r <= C.CJ - 2) for r in range(C.R)]
     store_cols = (tx >= 1) & (tx <= C.TX - 2)
+    # SHFL variant: the k-1 / k+1 cells come from the adjacent LANE's registers except at a warp's edge
+    # lanes, a row's end threads and the last worker (whose next lane is a padding thread)
+    lane = tid & 31
+    edge_lo = (lane == 0) | (tx == 0)
+    edge_hi = (lane == 31) | (tx == C.TX - 1) | (tid >= C.WORKERS - 1)
+
+    def nbr_cells(pairs, lo_loaded, hi_loaded):
+        """pairs: (WORKERS, 2) registers of one row; *_loaded: what the shared-memory load returns"""
+        if not shfl:
+            return lo_loaded, hi_loaded
+        up_lane = np.concatenate([[np.nan], pairs[:-1, 1]])    # __shfl_up(y, 1)
+        dn_lane = np.concatenate([pairs[1:, 0], [np.nan]])     # __shfl_down(x, 1)
+        return np.where(edge_lo, lo_loaded, up_lane), np.where(edge_hi, hi_loaded, dn_lane)
 
     def acc(a, wt, v, u=False):
         # numpy float64: separately rounded multiply and add; the unit kernel skips the multiply
@@ -154,8 +167,7 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
             kp = np.empty((C.R, C.WORKERS))
             for r in range(C.R):
                 c[r] = lds_v2(smem, sb + (1 + r) * P)
-                km[r] = lds_f64(smem, sb + (1 + r) * P - 8)
-                kp[r] = lds_f64(smem, sb + (1 + r) * P + 16)
+                km[r], kp[r] = nbr_cells(c[r], lds_f64(smem, sb + (1 + r) * P - 8), lds_f64(smem, sb + (1 + r) * P + 16))
             l1 = np.empty_like(c)
             for r in range(C.R):
                 l1[r, :, 0] = acc(part1[r, :, 0], w6, c[r, :, 0], True)
@@ -192,8 +204,7 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
             up1 = lds_v2(xb, tb)
             dn1 = lds_v2(xb, tb + (C.R + 1) * P)
             for r in range(C.R):
-                km[r] = lds_f64(xb, tb + (1 + r) * P - 8)
-                kp[r] = lds_f64(xb, tb + (1 + r) * P + 16)
+                km[r], kp[r] = nbr_cells(l1[r], lds_f64(xb, tb + (1 + r) * P - 8), lds_f64(xb, tb + (1 + r) * P + 16))
             for r in range(C.R):
                 jm = up1 if r == 0 else l1[r - 1]
                 jp = dn1 if r == C.R - 1 else l1[r + 1]

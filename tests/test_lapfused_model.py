@@ -34,6 +34,17 @@ def test_model_single_slab(shape, BJ, R, ci, unit):
     assert np.array_equal(out, two_applies(x, w))
 
 
+@pytest.mark.parametrize("shape,BJ,R", [((4, 32, 256), 16, 6), ((3, 16, 128), 16, 3)])
+def test_model_shuffled_k_neighbours(shape, BJ, R):
+    """The experimental SHFL variant (k-1 / k+1 from the adjacent lanes, loads only at warp and row edges)."""
+    rng = np.random.default_rng(SEED + 3)
+    x = rng.random(shape)
+    w = [1.0, 1.0, 1.0, -6.0, 1.0, 1.0, 1.0]
+    out = np.full(shape, np.nan)
+    fused_two_applies(x, w, 0, shape[0], 2, Cfg(BJ, R), 4, 0, shape[0], out, unit=True, shfl=True)
+    assert np.array_equal(out, two_applies(x, w))
+
+
 def test_model_64_cell_tiles():
     rng = np.random.default_rng(SEED + 2)
     x = rng.random((4, 16, 192))

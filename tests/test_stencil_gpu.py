@@ -260,6 +260,26 @@ def test_fused_two_applies_every_tile_configuration(gpu_fb, cfg, general, monkey
     assert np.array_equal(out, _applies(a, off, w, 4))
 
 
+@pytest.mark.parametrize("cfg", [12, 13])
+def test_fused_two_applies_experimental_configurations(gpu_fb, cfg, monkeypatch):
+    """Tile configurations that are compiled but have not been timed or made selectable by default (shuffled
+    k-neighbours).  Opt in with FDB_TEST_EXPERIMENTAL=1 when trying them on a B200."""
+    import os
+    if os.environ.get("FDB_TEST_EXPERIMENTAL", "0") == "0":
+        pytest.skip("experimental tile configurations: set FDB_TEST_EXPERIMENTAL=1")
+    monkeypatch.setenv("FDB_LAPF_CFG", str(cfg))
+    monkeypatch.setenv("FDB_TMA_CI", "3")
+    rng = np.random.default_rng(SEED + 23)
+    a = rng.random((7, 32, 256)) - 0.5
+    off, w = oracle.laplacian_stencil(3)
+    for weights in (w, rng.standard_normal(7)):
+        with gpu_fb.Filter(a.shape, [0.0] * 3, [1.0] * 3, as_dict(off, weights)) as fl:
+            fl.set_input(a)
+            fl.iterate(4)
+            out = fl.get()
+        assert np.array_equal(out, _applies(a, off, weights, 4))
+
+
 def test_fused_laplacian_driver_sequence_128(gpu_fb):
     """laplacian.cxx:86-90 at 128^3 through the fused kernel: 10 x (apply; copyOutToIn) from the driver's
     input, amplified roundoff and all."""
