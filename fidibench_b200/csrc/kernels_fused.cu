@@ -351,6 +351,9 @@ const FusedConfig kFused3[] = {
     make_fused<FusedCfg<3, 21, 3, 6>>("t3_cj21_r3_s6"),
     make_fused<FusedCfg<3, 20, 5, 6>>("t3_cj20_r5_s6"),
     make_fused<FusedCfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
+    // not yet timed on a B200: two rows per thread, 19 consumer warps at 96 registers (more warps in flight)
+    make_fused<FusedCfg<3, 18, 2, 4>>("t3_cj18_r2_s4"),
+    make_fused<FusedCfg<3, 18, 2, 3>>("t3_cj18_r2_s3"),
 };
 const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
