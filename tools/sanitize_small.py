@@ -35,4 +35,22 @@ for kern in (fb.FDB_KERNEL_TMA, fb.FDB_KERNEL_GENERIC):
         for _ in range(3):
             r = oracle.c.stencil_apply(r, off, w)
         assert np.array_equal(fl.get(), r)
+# fused two-apply 7-point kernel (unit-weight and general kernels), odd count ends on the single-apply kernel
+y = rng.random((5, 16, 128)) - 0.5
+for weights in (w, rng.standard_normal(7)):
+    stw = {tuple(int(v) for v in o): float(c) for o, c in zip(off, weights)}
+    with fb.Filter(y.shape, [0.0] * 3, [1.0] * 3, stw) as fl:
+        assert fl.fuse() == 2
+        fl.set_input(y)
+        fl.iterate(3)
+        r = y
+        for _ in range(3):
+            r = oracle.c.stencil_apply(r, off, weights)
+        assert np.array_equal(fl.get(), r)
+# negative velocities on the mirrored grid (mirror_kernel + tiled kernels)
+c = rng.random((6, 10, 36))
+with fb.Upwind([-1.0, 1.0, -0.5], [1.0] * 3, c.shape) as up:
+    up.set_field(c)
+    up.advect(4, 0.004)
+    assert np.array_equal(up.field(), oracle.c.upwind_advect(c, 4, velocity=[-1.0, 1.0, -0.5], dt=0.004))
 print("sanitize_small ok")
