@@ -71,12 +71,14 @@ _SIGS = {
     "fdb_upwind_set_slab": (i32, [vp, vp]),
     "fdb_upwind_set_slab_async": (i32, [vp, vp]),
     "fdb_upwind_reset": (i32, [vp]),
+    "fdb_upwind_fill_random": (i32, [vp, C.c_uint64]),
     "fdb_upwind_advect": (i32, [vp, i64, dbl]),
     "fdb_upwind_advect_async": (i32, [vp, i64, dbl]),
     "fdb_upwind_sync": (i32, [vp]),
     "fdb_upwind_default_dt": (i32, [vp, p_dbl]),
     "fdb_upwind_checksum": (i32, [vp, p_dbl]),
     "fdb_upwind_std": (i32, [vp, p_dbl]),
+    "fdb_upwind_plane_sums": (i32, [vp, vp, i64, p_i64]),
     "fdb_upwind_get_field": (i32, [vp, vp]),
     "fdb_upwind_get_slab": (i32, [vp, vp]),
     "fdb_upwind_set_kernel": (i32, [vp, i32]),
@@ -90,10 +92,13 @@ _SIGS = {
     "fdb_stencil_local_range": (i32, [vp, p_i64, p_i64]),
     "fdb_stencil_set_input": (i32, [vp, vp, i32]),
     "fdb_stencil_set_input_slab": (i32, [vp, vp]),
+    "fdb_stencil_set_input_separable": (i32, [vp, p_vp]),
+    "fdb_stencil_fill_random": (i32, [vp, C.c_uint64]),
     "fdb_stencil_apply": (i32, [vp]),
     "fdb_stencil_swap": (i32, [vp]),
     "fdb_stencil_iterate": (i32, [vp, i64]),
     "fdb_stencil_checksum": (i32, [vp, i32, p_dbl]),
+    "fdb_stencil_sumsq": (i32, [vp, i32, p_dbl]),
     "fdb_stencil_get": (i32, [vp, i32, vp, i32]),
     "fdb_stencil_get_slab": (i32, [vp, i32, vp]),
     "fdb_stencil_set_kernel": (i32, [vp, i32]),

@@ -456,6 +456,20 @@ int fdb_upwind_reset(fdb_upwind* h) {
   FDB_GUARD_END
 }
 
+int fdb_upwind_fill_random(fdb_upwind* h, uint64_t seed) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  Field* f = &h->field;
+  if (!h->any_flip) {
+    FDB_TRY(field_fill_random(f, f->cur, seed, /*publish=*/true));
+  } else {  // the hash is a function of the LOGICAL cell index: fill the spare buffer, mirror it into place
+    FDB_TRY(field_fill_random(f, 1 - f->cur, seed, /*publish=*/false));
+    FDB_TRY(field_mirror(f, 1 - f->cur, f->cur, h->flip, /*publish=*/true));
+  }
+  return field_sync(f);
+  FDB_GUARD_END
+}
+
 int fdb_upwind_default_dt(const fdb_upwind* h, double* dt) {
   if (!h || !dt) return set_error(FDB_E_INVALID, "null argument");
   // ref: upwind.cxx:186-192
@@ -569,6 +583,19 @@ int fdb_upwind_checksum(fdb_upwind* h, double* sum) {
   FDB_GUARD_BEGIN
   if (!h || !sum) return set_error(FDB_E_INVALID, "null argument");
   return field_sum(&h->field, h->field.cur, sum);
+  FDB_GUARD_END
+}
+
+int fdb_upwind_plane_sums(fdb_upwind* h, double* sums, int64_t capacity, int64_t* count) {
+  FDB_GUARD_BEGIN
+  if (!h || !count) return set_error(FDB_E_INVALID, "null argument");
+  const Geometry& g = h->field.geo;
+  *count = g.n[0];
+  if (!sums) return FDB_OK;  // size query
+  if (capacity < g.n[0]) return set_error(FDB_E_INVALID, "room for %lld plane sums, %lld needed", (long long)capacity, (long long)g.n[0]);
+  FDB_TRY(field_plane_sums(&h->field, h->field.cur, sums));
+  if (h->flip[0]) std::reverse(sums, sums + g.n[0]);  // the device holds axis 0 mirrored
+  return FDB_OK;
   FDB_GUARD_END
 }
 
@@ -706,6 +733,27 @@ int fdb_stencil_set_input_slab(fdb_stencil* h, const double* host_slab) {
   FDB_GUARD_END
 }
 
+int fdb_stencil_fill_random(fdb_stencil* h, uint64_t seed) {
+  FDB_GUARD_BEGIN
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  // the hash runs over the device's row-major cell order; a single-plane 2-D handle has the same order
+  FDB_TRY(field_fill_random(&h->field, h->field.cur, seed, /*publish=*/true));
+  h->out_valid = false;
+  return field_sync(&h->field);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_set_input_separable(fdb_stencil* h, const double* const* factors) {
+  FDB_GUARD_BEGIN
+  if (!h || !factors) return set_error(FDB_E_INVALID, "null argument");
+  for (int j = 0; j < h->ndims; ++j)
+    if (!factors[j]) return set_error(FDB_E_INVALID, "null factor array for axis %d", j);
+  FDB_TRY(field_fill_separable(&h->field, h->field.cur, h->ndims, factors, h->dims));
+  h->out_valid = false;
+  return field_sync(&h->field);
+  FDB_GUARD_END
+}
+
 int fdb_stencil_get_kernel(const fdb_stencil* h, int* kernel) {
   if (!h || !kernel) return set_error(FDB_E_INVALID, "null argument");
   const bool can = stencil_lap7_supported(h->field, h->br);
@@ -838,6 +886,15 @@ int fdb_stencil_checksum(fdb_stencil* h, int which, double* sum) {
   int p = 0;
   FDB_TRY(stencil_buffer(h, which, &p));
   return field_sum(&h->field, p, sum);
+  FDB_GUARD_END
+}
+
+int fdb_stencil_sumsq(fdb_stencil* h, int which, double* sumsq) {
+  FDB_GUARD_BEGIN
+  if (!h || !sumsq) return set_error(FDB_E_INVALID, "null argument");
+  int p = 0;
+  FDB_TRY(stencil_buffer(h, which, &p));
+  return field_sqdev(&h->field, p, 0.0, sumsq);
   FDB_GUARD_END
 }
 

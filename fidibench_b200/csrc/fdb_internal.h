@@ -154,6 +154,10 @@ int field_set_stream(Field* f, void* stream);
 int field_upload(Field* f, int p, const double* host_global, const double* host_slab, bool async = false);
 int field_download(Field* f, int p, double* host_global, double* host_slab);
 int field_fill_delta(Field* f, int p, int64_t cell = 0);  // zero field, global cell `cell` = 1
+// device-side synthetic inputs (no host copy): hash of the global cell index / separable product of 1-D factors
+// (x[j] = HOST array of the extent of reference axis j); both publish buf[p] as the current field when `publish`
+int field_fill_random(Field* f, int p, uint64_t seed, bool publish);
+int field_fill_separable(Field* f, int p, int nd, const double* const* x_host, const int64_t* extents);
 // single-slab fields: buf[dst] = buf[src] mirrored along the flagged axes, on the main stream; buf[dst]
 // becomes the current field when `publish`
 int field_mirror(Field* f, int src, int dst, const bool* flip, bool publish);
@@ -168,6 +172,7 @@ int field_sync(Field* f);
 // dist mode, every rank gets the result)
 int field_sum(Field* f, int p, double* out);
 int field_sqdev(Field* f, int p, double mean, double* out);
+int field_plane_sums(Field* f, int p, double* planes_out);  // geo.n[0] per-plane sums, global plane order
 
 // one sweep of a stencil kernel over every slab: boundary planes first (their halos start
 // travelling while the interior is computed), ghosts of the new field exchanged, buffers not
@@ -227,6 +232,9 @@ int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode,
                       double* partial, double* plane_sums, cudaStream_t s);
 int64_t reduce_partials_per_plane(int64_t plane);
 int launch_fill(double* p, int64_t n, double v, cudaStream_t s);
+int launch_fill_random(double* p, int64_t n, uint64_t seed, int64_t g0, cudaStream_t s);
+int launch_separable(double* out, int64_t i_lo, int64_t nplanes, int64_t n1, int64_t n2, int nd,
+                     const double* const* x, const int* ax, cudaStream_t s);
 int launch_permute(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, cudaStream_t s);
 int launch_mirror(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, const bool* flip, cudaStream_t s);
 

@@ -482,7 +482,9 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   if (ci > planes) ci = planes;
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
-  const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
+  if (const int cap = fz_env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;
   C->kernel<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const FusedMaps*>(sl.fused_maps[X]), a);
   count_launch();
   FDB_CUDA(cudaGetLastError());

@@ -112,6 +112,48 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(double* p, int64_t n, do
     p[t] = v;
 }
 
+// Device-side synthetic input (bench/parity fields without a host copy): cell g of the GLOBAL row-major field
+// gets u(seed, g) = (splitmix64(seed + (g+1)*0x9E3779B97F4A7C15) >> 11) * 2^-53, a pure function of the global
+// index, so the field does not depend on how planes are spread over devices (tests restate it with numpy).
+__device__ __forceinline__ double hash_u01(uint64_t seed, uint64_t g) {
+  uint64_t z = seed + (g + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * 0x1.0p-53;  // exact: 53 bits
+}
+__global__ void __launch_bounds__(kThreads) fill_random_kernel(double* p, int64_t n, uint64_t seed, int64_t g0) {
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * kThreads)
+    p[t] = hash_u01(seed, (uint64_t)(g0 + t));
+}
+
+// Separable input: cell (i, j, k) = ((1 * xa[.]) * xb[.]) * xc[.] in the REFERENCE's axis order -- the product
+// Filter::setInData accumulates for laplacian.cxx's func (ref: laplacian.cxx:22-28, Filter.cpp:103-112), with the
+// 1-D factors sin(2 pi x) evaluated on the host (same libm, same bits) and only 8 B x (d0+d1+d2) uploaded.
+// ax[] = internal axis of reference axis 0..nd-1.
+struct SeparableArgs {
+  double* out;
+  int64_t i_lo, nplanes, n1, n2;
+  const double* x[3];
+  int ax[3];
+  int nd;
+};
+__global__ void __launch_bounds__(kThreads) separable_kernel(SeparableArgs a) {
+  const int64_t plane = a.n1 * a.n2;
+  const int64_t total = a.nplanes * plane;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * kThreads) {
+    int64_t idx[3];
+    idx[0] = a.i_lo + t / plane;
+    idx[1] = (t % plane) / a.n2;
+    idx[2] = t % a.n2;
+    double res = 1.0;
+    for (int j = 0; j < a.nd; ++j) res = __dmul_rn(res, a.x[j][idx[a.ax[j]]]);
+    a.out[t] = res;
+  }
+}
+
 // out[k][j][i] (row-major n2 x n1 x n0) = in[i][j][k] (row-major n0 x n1 x n2):
 // converts between row-major and Filter's column-major storage (Filter.cpp:50).
 __global__ void __launch_bounds__(kThreads) permute210_kernel(const double* __restrict__ in,
@@ -285,6 +327,26 @@ int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode,
 int launch_fill(double* p, int64_t n, double v, cudaStream_t s) {
   if (n <= 0) return FDB_OK;
   fill_kernel<<<grid_for(n), kThreads, 0, s>>>(p, n, v);
+  count_launch();
+  FDB_CUDA(cudaGetLastError());
+  return FDB_OK;
+}
+
+int launch_fill_random(double* p, int64_t n, uint64_t seed, int64_t g0, cudaStream_t s) {
+  if (n <= 0) return FDB_OK;
+  fill_random_kernel<<<grid_for(n), kThreads, 0, s>>>(p, n, seed, g0);
+  count_launch();
+  FDB_CUDA(cudaGetLastError());
+  return FDB_OK;
+}
+
+int launch_separable(double* out, int64_t i_lo, int64_t nplanes, int64_t n1, int64_t n2, int nd,
+                     const double* const* x, const int* ax, cudaStream_t s) {
+  if (nplanes <= 0) return FDB_OK;
+  SeparableArgs a;
+  a.out = out; a.i_lo = i_lo; a.nplanes = nplanes; a.n1 = n1; a.n2 = n2; a.nd = nd;
+  for (int j = 0; j < 3; ++j) { a.x[j] = j < nd ? x[j] : nullptr; a.ax[j] = j < nd ? ax[j] : 0; }
+  separable_kernel<<<grid_for(nplanes * n1 * n2), kThreads, 0, s>>>(a);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;

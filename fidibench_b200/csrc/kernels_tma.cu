@@ -565,7 +565,9 @@ int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, 
   if (ci > planes) ci = planes;
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
-  const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
+  if (const int cap = env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;
   const int p = X;
   C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p],
                                                      sl.tm_glo[p], a);
@@ -711,7 +713,9 @@ int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend
   if (ci > planes) ci = planes;
   a.ci = (int)ci;
   a.nwork = tiles * ((planes + ci - 1) / ci);
-  const int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
+  // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
+  if (const int cap = env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;
   const int p = X;
   C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p],
                                                      sl.tm_ghi[p], a);

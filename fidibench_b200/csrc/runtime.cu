@@ -453,6 +453,41 @@ int field_fill_delta(Field* f, int p, int64_t cell) {
   return field_publish(f, p);
 }
 
+int field_fill_random(Field* f, int p, uint64_t seed, bool publish) {
+  FDB_TRY(field_sync(f));
+  const int64_t plane = f->geo.plane();
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    FDB_TRY(launch_fill_random(f->body(d, p), s.nloc() * plane, seed, s.lo * plane, s.s_main));
+  }
+  return publish ? field_publish(f, p) : FDB_OK;
+}
+
+int field_fill_separable(Field* f, int p, int nd, const double* const* x_host, const int64_t* extents) {
+  FDB_TRY(field_sync(f));
+  int64_t total = 0;
+  for (int j = 0; j < nd; ++j) total += extents[j];
+  std::vector<double> packed((size_t)total);
+  for (int j = 0, o = 0; j < nd; o += (int)extents[j], ++j) memcpy(packed.data() + o, x_host[j], (size_t)extents[j] * sizeof(double));
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    double* dx = nullptr;
+    FDB_CUDA(cudaMalloc(&dx, (size_t)total * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(dx, packed.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice, s.s_main);
+    const double* x[3] = {nullptr, nullptr, nullptr};
+    for (int j = 0, o = 0; j < nd; o += (int)extents[j], ++j) x[j] = dx + o;
+    int rc = (e == cudaSuccess) ? launch_separable(f->body(d, p), s.lo, s.nloc(), f->geo.n[1], f->geo.n[2], nd, x,
+                                                   f->geo.axis_of, s.s_main)
+                                : set_error(FDB_E_CUDA, "H2D copy: %s", cudaGetErrorString(e));
+    cudaStreamSynchronize(s.s_main);  // `packed` and dx are released below
+    cudaFree(dx);
+    FDB_TRY(rc);
+  }
+  return field_publish(f, p);
+}
+
 int field_mirror(Field* f, int src, int dst, const bool* flip, bool publish) {
   if (!f->single() || src == dst) return set_error(FDB_E_STATE, "mirroring needs a single-slab field and two buffers");
   Slab& s = f->slabs[0];
@@ -730,7 +765,7 @@ int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n) {
 }
 
 // ---- reductions -------------------------------------------------------------------------
-static int field_reduce(Field* f, int p, int mode, double mean, double* out) {
+static int field_reduce(Field* f, int p, int mode, double mean, double* out, double* planes_out = nullptr) {
   const int64_t plane = f->geo.plane();
   const int64_t n0 = f->geo.n[0];
   std::vector<double> sums((size_t)n0, 0.0);
@@ -767,9 +802,12 @@ static int field_reduce(Field* f, int p, int mode, double mean, double* out) {
   }
   double acc = 0.0;
   for (int64_t i = 0; i < n0; ++i) acc += sums[(size_t)i];  // global plane order
-  *out = acc;
+  if (out) *out = acc;
+  if (planes_out) memcpy(planes_out, sums.data(), (size_t)n0 * sizeof(double));
   return FDB_OK;
 }
+
+int field_plane_sums(Field* f, int p, double* planes_out) { return field_reduce(f, p, 0, 0.0, nullptr, planes_out); }
 
 int field_sum(Field* f, int p, double* out) { return field_reduce(f, p, 0, 0.0, out); }
 int field_sqdev(Field* f, int p, double mean, double* out) { return field_reduce(f, p, 1, mean, out); }

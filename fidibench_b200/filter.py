@@ -30,6 +30,7 @@ class Filter:
         self.xmaxs = [float(x) for x in xmaxs]
         self.stencil = {tuple(int(o) for o in k): float(v) for k, v in stencil.items()}
         self.comm = comm
+        self.ngpus = int(ngpus)
         self._h = C.c_void_p()
         self.validDecomp = False
         offs = np.array(list(self.stencil.keys()), dtype=np.int32).reshape(len(self.stencil), self.ndims)
@@ -63,7 +64,8 @@ class Filter:
         return self.comm.rank if self.comm is not None else 0
 
     def getNumProcs(self) -> int:
-        return self.comm.nranks if self.comm is not None else 1
+        """Slabs of the ring: the comm's ranks, or the devices of an in-process handle (as drivers/Filter.hpp)."""
+        return self.comm.nranks if self.comm is not None else self.ngpus
 
     def isDecompValid(self) -> bool:
         return self.validDecomp
@@ -97,6 +99,12 @@ class Filter:
         check(lib.fdb_stencil_checksum(self._h, which, C.byref(out)))
         return float(out.value)
 
+    def sumsq(self, inOrOut: str = "output") -> float:
+        which = _lib.FDB_INPUT if inOrOut == "input" else _lib.FDB_OUTPUT
+        out = C.c_double()
+        check(lib.fdb_stencil_sumsq(self._h, which, C.byref(out)))
+        return float(out.value)
+
     # -- harness ---------------------------------------------------------------------------
     def set_input(self, field: np.ndarray, layout: int = _lib.FDB_ROW_MAJOR) -> None:
         a = np.ascontiguousarray(field, dtype=np.float64)
@@ -107,7 +115,42 @@ class Filter:
     def set_input_slab(self, slab: np.ndarray) -> None:
         """Only this handle's planes [lo,hi) (one-process-per-GPU runs on grids too big for one host array)."""
         a = np.ascontiguousarray(slab, dtype=np.float64)
+        if a.size != self.slab_cells():
+            raise ValueError(f"expected a slab of {self.slab_cells()} cells, got {a.size}")
         check(lib.fdb_stencil_set_input_slab(self._h, a.ctypes.data_as(C.c_void_p)))
+
+    def slab_cells(self) -> int:
+        ntot = int(np.prod(self.globalDims, dtype=np.int64))
+        return ntot if self.ndims == 1 else (self.hi - self.lo) * (ntot // self.globalDims[0])
+
+    def set_input_separable(self, factors) -> None:
+        """Input = product over the axes (reference order) of 1-D factors, evaluated on the device: what
+        setInData(func) yields for laplacian.cxx's func when factors[j][i] = sin(2 pi x_j(i))."""
+        arrs = [np.ascontiguousarray(f, dtype=np.float64) for f in factors]
+        if len(arrs) != self.ndims or any(a.size != n for a, n in zip(arrs, self.globalDims)):
+            raise ValueError("one factor array of globalDims[j] values per axis")
+        ptrs = (C.c_void_p * self.ndims)(*[a.ctypes.data for a in arrs])
+        check(lib.fdb_stencil_set_input_separable(self._h, ptrs))
+
+    def laplacian_factors(self):
+        """The 1-D factors of the laplacian driver's input function, evaluated on the host with libm's sin
+        (ref: laplacian.cxx:22-28 on Filter::getPosition, Filter.cpp:103-112)."""
+        import math
+        out = []
+        for j in range(self.ndims):
+            delta = (self.xmaxs[j] - self.xmins[j]) / float(self.globalDims[j])
+            out.append(np.array([math.sin(2.0 * math.pi * (self.xmins[j] + (i + 0.5) * delta))
+                                 for i in range(self.globalDims[j])]))
+        return out
+
+    def fill_random(self, seed: int) -> None:
+        check(lib.fdb_stencil_fill_random(self._h, C.c_uint64(seed)))
+
+    def get_slab(self, which: int = _lib.FDB_OUTPUT) -> np.ndarray:
+        shape = self.globalDims if self.ndims == 1 else (self.hi - self.lo,) + self.globalDims[1:]
+        out = np.zeros(shape, dtype=np.float64)
+        check(lib.fdb_stencil_get_slab(self._h, which, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def saveVTK(self, filename: str) -> None:
         """ASCII structured-grid dump of the output data, layout of cxx/writeVTK.cpp:12-95."""

@@ -53,6 +53,14 @@ class Upwind:
         check(lib.fdb_upwind_std(self._h, C.byref(out)))
         return float(out.value)
 
+    def plane_sums(self) -> np.ndarray:
+        """Per-plane sums along axis 0 (the partial sums behind checksum())."""
+        n = C.c_int64()
+        check(lib.fdb_upwind_plane_sums(self._h, None, 0, C.byref(n)))
+        out = np.zeros(int(n.value), dtype=np.float64)
+        check(lib.fdb_upwind_plane_sums(self._h, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
+        return out
+
     def saveVTK(self, filename: str) -> None:
         """ASCII rectilinear-grid dump with the layout of upwind/cxx/saveVTK.h."""
         f = self.field().reshape(-1)
@@ -115,6 +123,10 @@ class Upwind:
     def reset(self) -> None:
         check(lib.fdb_upwind_reset(self._h))
 
+    def fill_random(self, seed: int) -> None:
+        """Seeded synthetic field generated on the device (see fdb_upwind_fill_random)."""
+        check(lib.fdb_upwind_fill_random(self._h, C.c_uint64(seed)))
+
     def field(self) -> np.ndarray:
         """Whole-domain field (row-major); in dist mode only planes [lo,hi) are filled."""
         out = np.zeros(self.numCells, dtype=np.float64)
@@ -126,6 +138,12 @@ class Upwind:
         out = np.zeros(shape, dtype=np.float64)
         check(lib.fdb_upwind_get_slab(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def slab_into(self, out: np.ndarray) -> None:
+        """Copy this handle's planes into a caller-owned C-contiguous float64 array (e.g. pinned memory)."""
+        if out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"] or out.size != self.slab_cells():
+            raise ValueError("slab_into needs a C-contiguous float64 array of slab_cells() elements")
+        check(lib.fdb_upwind_get_slab(self._h, out.ctypes.data_as(C.c_void_p)))
 
     def advect_async(self, numTimeSteps: int, deltaTime: float) -> None:
         check(lib.fdb_upwind_advect_async(self._h, int(numTimeSteps), float(deltaTime)))

@@ -122,6 +122,10 @@ int fdb_upwind_set_slab(fdb_upwind *h, const double *host_slab);
 int fdb_upwind_set_slab_async(fdb_upwind *h, const double *host_slab);
 /* reset to the ctor's initial condition (delta at cell 0), upwind.cxx:45-48 */
 int fdb_upwind_reset(fdb_upwind *h);
+/* synthetic input generated ON the device (no host copy; benches and parity checks at sizes where a host
+ * field is unwieldy): cell g of the global row-major field <- (splitmix64(seed + (g+1)*0x9E3779B97F4A7C15)
+ * >> 11) * 2^-53, uniform in [0,1) and independent of the slab partition. */
+int fdb_upwind_fill_random(fdb_upwind *h, uint64_t seed);
 
 /* ref: Upwind::advect(numTimeSteps, deltaTime), upwind.cxx:51-86 */
 int fdb_upwind_advect(fdb_upwind *h, int64_t numTimeSteps, double deltaTime);
@@ -133,6 +137,11 @@ int fdb_upwind_default_dt(const fdb_upwind *h, double *dt);
 
 /* ref: Upwind::checksum(), upwind.cxx:91-93 (collective in dist mode; every rank gets the sum) */
 int fdb_upwind_checksum(fdb_upwind *h, double *sum);
+/* the per-plane sums behind the checksum: sums[i] = sum of plane i of axis 0 (fixed-shape tree on the device, the
+ * checksum is their sequential sum); *count <- planes (numCells[0] for 3-D, 1 for a 1-D field); sums == NULL only
+ * queries the count.  Collective in dist mode, every rank gets all planes.  A cheap size-independent parity
+ * probe for fields too large to copy back. */
+int fdb_upwind_plane_sums(fdb_upwind *h, double *sums, int64_t capacity, int64_t *count);
 /* ref: Upwind::std(), upwind.cxx:95-103 */
 int fdb_upwind_std(fdb_upwind *h, double *stddev);
 /* whole-domain copy-out, row-major (feeds the host-side saveVTK/print);
@@ -174,6 +183,14 @@ int fdb_stencil_local_range(const fdb_stencil *h, int64_t *lo, int64_t *hi);
  * evaluates its callback on the host and hands the array over (whole domain) */
 int fdb_stencil_set_input(fdb_stencil *h, const double *host_field, int layout);
 int fdb_stencil_set_input_slab(fdb_stencil *h, const double *host_slab);
+/* Separable input evaluated on the device: cell (i_0..i_{nd-1}) <- ((1 * factors[0][i_0]) * factors[1][i_1]) * ...
+ * in the reference's axis order, i.e. what Filter::setInData accumulates for laplacian.cxx's
+ * func = prod_j sin(2 pi x_j) (ref: laplacian.cxx:22-28, Filter.cpp:103-112,131-160) when the driver evaluates
+ * the 1-D factors sin(2 pi x_j(i)) on the host: the same bits as the host-evaluated field, with
+ * 8 B x (d_0 + ... + d_{nd-1}) uploaded instead of 8 B x d_0 ... d_{nd-1}.  factors[j] holds globalDims[j] doubles. */
+int fdb_stencil_set_input_separable(fdb_stencil *h, const double *const *factors);
+/* same synthetic field as fdb_upwind_fill_random, over the handle's row-major cell order */
+int fdb_stencil_fill_random(fdb_stencil *h, uint64_t seed);
 /* ref: Filter::applyFilter(), Filter.cpp:191-263 */
 int fdb_stencil_apply(fdb_stencil *h);
 /* ref: Filter::copyOutToIn(), Filter.cpp:440-463 -- O(1): the buffers swap
@@ -190,6 +207,8 @@ int fdb_stencil_set_fuse(fdb_stencil *h, int applies_per_sweep);
 int fdb_stencil_get_fuse(const fdb_stencil *h, int *applies_per_sweep);
 /* ref: Filter::computeCheckSum("input"|"output"), Filter.cpp:465-485 */
 int fdb_stencil_checksum(fdb_stencil *h, int which, double *sum);
+/* sum of squares of the input or output data, same deterministic reduction (a norm for parity probes) */
+int fdb_stencil_sumsq(fdb_stencil *h, int which, double *sumsq);
 int fdb_stencil_get(fdb_stencil *h, int which, double *host_field, int layout);
 int fdb_stencil_get_slab(fdb_stencil *h, int which, double *host_slab);
 int fdb_stencil_set_kernel(fdb_stencil *h, int kernel);

@@ -273,6 +273,18 @@ def np_stencil_apply(field, offsets, weights):
     return out
 
 
+def hash_field(seed, shape):
+    """numpy restatement of the device-side synthetic fill (fidibench_b200/csrc/kernels_generic.cu: hash_u01):
+    cell g of the row-major field = (splitmix64(seed + (g+1)*0x9E3779B97F4A7C15) >> 11) * 2^-53."""
+    n = int(np.prod(shape, dtype=np.int64))
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (np.arange(n, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53).reshape(tuple(int(x) for x in shape))
+
+
 def laplacian_stencil(ndims):
     """laplacian/cxx/laplacian.cxx:55-65 (insertion order; the map sorts it)."""
     offs, w = [[0] * ndims], [-2.0 * ndims]

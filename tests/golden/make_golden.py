@@ -19,6 +19,31 @@ import oracle  # noqa: E402
 SEED = 20261017
 
 
+def bench_parity(r):
+    # bench.py's untimed parity block (every N in 1, 2, 4, 8): the device-generated hash field (oracle.hash_field
+    # restates it) on (16 N) x 48 x 256 advected 11 steps by the untouched upwind.cxx, and on (16 N) x 32 x 256
+    # through 5 x (applyFilter; copyOutToIn) of the untouched Filter.cpp with the 7-point Laplacian; stored as one
+    # SHA-256 per plane of the reference's output (the fields themselves would be 25 MB)
+    import hashlib
+    import json
+    par = {"seed": SEED, "upwind_steps": 11, "stencil_iters": 5, "upwind": {}, "stencil": {}}
+    off3, w3 = oracle.laplacian_stencil(3)
+    for n in (1, 2, 4, 8):
+        shape = (16 * n, 48, 256)
+        a = oracle.hash_field(SEED, shape)
+        g = r.upwind_run(shape, par["upwind_steps"], init=a)
+        par["upwind"][str(n)] = {"dims": list(shape), "dt": g["dt"], "checksum": g["checksum"],
+                                 "planes": [hashlib.sha256(p.tobytes()).hexdigest() for p in g["field"]]}
+        shape = (16 * n, 32, 256)
+        a = oracle.hash_field(SEED, shape)
+        g = r.filter_run(shape, off3, w3, init=a, niter=par["stencil_iters"])
+        par["stencil"][str(n)] = {"dims": list(shape),
+                                  "planes": [hashlib.sha256(p.tobytes()).hexdigest() for p in g["field"]]}
+    with open(os.path.join(HERE, "bench_parity.json"), "w") as fh:
+        json.dump(par, fh)
+
+
+
 def main():
     r = oracle.ref()
     rng = np.random.default_rng(SEED)
@@ -97,6 +122,8 @@ def main():
     gt = r.filter_run([8, 8], offt, wt, init=a, niter=1)
     np.savez_compressed(os.path.join(HERE, "stencil2d_8.npz"), init=a, out=gt["field"], offsets=offt, weights=wt)
 
+    bench_parity(r)
+
     # CubeDecomp's choices, for the record (we replace it with slabs)
     dec = {f"p{p}": np.array(r.cubedecomp(p, [128] * 3) or (0, 0, 0)) for p in (1, 2, 3, 4, 8, 16)}
     np.savez_compressed(os.path.join(HERE, "cubedecomp_128.npz"), **dec)
@@ -125,4 +152,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["bench_parity"]:   # only tests/golden/bench_parity.json
+        bench_parity(oracle.ref())
+    else:
+        main()

@@ -97,3 +97,28 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(import|from)\s+oracle|fdb_oracle|oracle/", src, flags=re.M):
                     offenders.append(os.path.join(base, fn))
     assert not offenders, f"product files reference the oracle: {offenders}"
+
+
+def test_bench_touches_the_oracle_only_in_its_cpu_baseline_leg():
+    """bench.py may import oracle only inside the reference arm / cpu_baseline functions; drivers never."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"reference_arm", "lap_cpu_baseline"}
+    offenders = []
+
+    def visit(node, fn):
+        for child in ast.iter_child_nodes(node):
+            name = child.name if isinstance(child, (ast.FunctionDef, ast.AsyncFunctionDef)) else fn
+            if isinstance(child, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in child.names):
+                if fn not in allowed:
+                    offenders.append((fn, child.lineno))
+            if isinstance(child, ast.ImportFrom) and (child.module or "").split(".")[0] == "oracle":
+                if fn not in allowed:
+                    offenders.append((fn, child.lineno))
+            visit(child, name)
+
+    visit(tree, "<module>")
+    assert not offenders, offenders
+    for fn in os.listdir(os.path.join(ROOT, "drivers")):
+        if fn.endswith((".cxx", ".hpp", ".py")):
+            assert "oracle" not in open(os.path.join(ROOT, "drivers", fn)).read(), fn
