@@ -86,6 +86,32 @@ class Filter {
     check(fdb_stencil_set_input(h_, a.data(), FDB_ROW_MAJOR));
   }
 
+  // setInData for a callback that is a product of one 1-D function over the axes (laplacian.cxx:22-28's func is
+  // prod_j sin(2 pi x_j)): the 1-D factors are evaluated here with the host's libm at Filter::getPosition's
+  // positions and multiplied out on the device in setInData's order -- the same bits as setInData(func), with
+  // 8 B x (d_0 + ... + d_{n-1}) crossing PCIe instead of the whole field.
+  void setInDataProduct(double (*f1)(double)) {
+    const size_t nd = globalDims_.size();
+    std::vector<std::vector<double> > fac(nd);
+    std::vector<const double*> ptr(nd);
+    for (size_t j = 0; j < nd; ++j) {
+      fac[j].resize(globalDims_[j]);
+      const double delta = (xmaxs_[j] - xmins_[j]) / double(globalDims_[j]);
+      for (size_t i = 0; i < globalDims_[j]; ++i) fac[j][i] = f1(xmins_[j] + (i + 0.5) * delta);
+      ptr[j] = fac[j].data();
+    }
+    check(fdb_stencil_set_input_separable(h_, ptr.data()));
+  }
+  // reproduce Filter.cpp:240's (int %= size_t) index wrap (non-periodic unless the extent is a power of two)
+  void setRefWrap(bool on) { check(fdb_stencil_set_ref_wrap(h_, on ? 1 : 0)); }
+  // binary dump of the output data: row-major FP64, native byte order, no header (full precision; the ASCII
+  // VTK file keeps six digits)
+  void saveRaw(const std::string& filename) {
+    const std::vector<double> f = getData(FDB_OUTPUT, FDB_ROW_MAJOR);
+    std::ofstream file(filename.c_str(), std::ios::binary);
+    file.write(reinterpret_cast<const char*>(f.data()), (std::streamsize)(f.size() * sizeof(double)));
+  }
+
   void applyFilter() { check(fdb_stencil_apply(h_)); }  // ref: Filter.cpp:191-263
   void copyOutToIn() { check(fdb_stencil_swap(h_)); }   // ref: Filter.cpp:440-463
   // niter x { applyFilter(); copyOutToIn(); } (ref: laplacian.cxx:86-90) in one call: the 3-D 7-point stencil

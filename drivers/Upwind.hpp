@@ -92,6 +92,13 @@ class Upwind {
     for (size_t i = 0; i < f.size(); ++i) std::cout << i << " " << f[i] << '\n';
   }
 
+  // binary dump of the field: row-major FP64, native byte order, no header
+  void saveRaw(const std::string& filename) const {
+    const std::vector<double> f = field();
+    std::ofstream file(filename.c_str(), std::ios::binary);
+    file.write(reinterpret_cast<const char*>(f.data()), (std::streamsize)(f.size() * sizeof(double)));
+  }
+
   // beyond the reference: host access to the device field, dt helper, timing
   std::vector<double> field() const {
     std::vector<double> f(ntot_);

@@ -19,6 +19,9 @@ static double func(const std::vector<double>& pos) {
   return res;
 }
 
+// func's 1-D factor: func(pos) = ((1 * sin1(pos[0])) * sin1(pos[1])) * ...
+static double sin1(double x) { return sin(2.0 * M_PI * x); }
+
 // ref: laplacian.cxx:55-65 -- 2*numDims+1 points, diagonal -2*numDims, neighbours +1, no 1/h^2 scaling
 static std::map<std::vector<int>, double> laplacianStencil(size_t numDims) {
   std::map<std::vector<int>, double> st;
@@ -41,6 +44,9 @@ int main(int argc, char** argv) {
   args.set("-vtk", false, "Write output to VTK file");
   args.set("-ngpus", 1, "Number of GPUs of this box sharing the domain (slabs along axis 0)");
   args.set("-numIter", 10, "Number of apply/copy iterations (the reference hard-codes 10)");
+  args.set("-raw", std::string(""), "Also dump the output data to this file (row-major FP64, no header)");
+  args.set("-refwrap", false, "Wrap indices as the reference does (int %= size_t: not periodic unless numCells is a power of two)");
+  args.set("-hostinit", false, "Evaluate the input function cell by cell on the host, as the reference does (same bits, slower)");
 
   const bool success = args.parse(argc, argv);
   const bool help = args.get<bool>("-h");
@@ -59,7 +65,11 @@ int main(int argc, char** argv) {
       fidib200::Filter fltr(globalDims, xmins, xmaxs, stencil, args.get<int>("-ngpus"));
       if (!fltr.isDecompValid()) std::cerr << "Decomposition is invalid\n";
       if (fltr.isDecompValid()) {
-        fltr.setInData(func);
+        if (args.get<bool>("-refwrap")) fltr.setRefWrap(true);
+        if (args.get<bool>("-hostinit"))
+          fltr.setInData(func);
+        else
+          fltr.setInDataProduct(sin1);  // same bits as setInData(func), the product runs on the device
         const auto tic = std::chrono::steady_clock::now();
         // repeat to improve statistics
         const size_t numIter = (size_t)args.get<int>("-numIter");
@@ -72,6 +82,8 @@ int main(int argc, char** argv) {
           std::cout << "Data will be written to file laplacian.vtk\n";
           fltr.saveVTK("laplacian.vtk");
         }
+        const std::string raw = args.get<std::string>("-raw");
+        if (!raw.empty()) fltr.saveRaw(raw);
         const double inSum = fltr.computeCheckSum("input");
         const double outSum = fltr.computeCheckSum("output");
         std::cout << "Laplace times min/max/avg: " << walltime << '/' << walltime << '/' << walltime << " [seconds]\n";

@@ -28,6 +28,14 @@ int main(int argc, char** argv) {
   args.set("-vz", 1.0, "Velocity along axis 2");
   args.set("-kernel", std::string("auto"), "auto | tma | generic");
   args.set("-timing", false, "Print GPU time, GCUPS and full-precision sums");
+  args.set("-raw", std::string(""), "Also dump the final field to this file (row-major FP64, no header)");
+  // the class supports anisotropic grids, the reference's main() does not expose them (upwind.cxx:174,182-183)
+  args.set("-nx", 0, "Cells along axis 0 (0 = -numCells)");
+  args.set("-ny", 0, "Cells along axis 1 (0 = -numCells)");
+  args.set("-nz", 0, "Cells along axis 2 (0 = -numCells)");
+  args.set("-lx", 1.0, "Domain length along axis 0");
+  args.set("-ly", 1.0, "Domain length along axis 1");
+  args.set("-lz", 1.0, "Domain length along axis 2");
 
   const bool success = args.parse(argc, argv);
   const bool help = args.get<bool>("-h");
@@ -39,6 +47,9 @@ int main(int argc, char** argv) {
 
     // same resolution in each direction
     std::vector<size_t> numCells(ndims, args.get<int>("-numCells"));
+    const char* perAxis[3] = {"-nx", "-ny", "-nz"};
+    for (int j = 0; j < ndims; ++j)
+      if (args.get<int>(perAxis[j]) > 0) numCells[j] = (size_t)args.get<int>(perAxis[j]);
     std::cout << "number of cells: ";
     for (size_t i = 0; i < numCells.size(); ++i) std::cout << ' ' << numCells[i];
     std::cout << '\n';
@@ -49,6 +60,9 @@ int main(int argc, char** argv) {
     velocity[1] = args.get<double>("-vy");
     velocity[2] = args.get<double>("-vz");
     std::vector<double> lengths(ndims, 1.0);
+    lengths[0] = args.get<double>("-lx");
+    lengths[1] = args.get<double>("-ly");
+    lengths[2] = args.get<double>("-lz");
 
     // dt from the Courant number, ref: upwind.cxx:186-192 (|v| so that a negative
     // velocity, which the class supports, still gives a positive step)
@@ -81,6 +95,7 @@ int main(int argc, char** argv) {
         std::cout << "std      : " << sd << '\n';
       }
       if (doVtk) up.saveVTK("up1.vtk");
+      if (!args.get<std::string>("-raw").empty()) up.saveRaw(args.get<std::string>("-raw"));
       if (args.get<bool>("-timing")) {
         const double ms = up.lastGpuMilliseconds();
         const double updates = double(numCells[0]) * numCells[1] * numCells[2] * numTimeSteps;

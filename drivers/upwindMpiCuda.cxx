@@ -53,6 +53,7 @@ int main(int argc, char** argv) {
   args.set("-numSteps", 10, "Number of time steps");
   args.set("-vtk", false, "Write output to VTK file");
   args.set("-ngpus", 1, "Number of GPUs of this box sharing the domain (slabs along axis 0)");
+  args.set("-raw", std::string(""), "Also dump the output data to this file (row-major FP64, no header)");
 
   const bool success = args.parse(argc, argv);
   const bool help = args.get<bool>("-h");
@@ -87,6 +88,8 @@ int main(int argc, char** argv) {
           std::cout << "Data will be written to file upMpi.vtk\n";
           fltr.saveVTK("upMpi.vtk");
         }
+        const std::string raw = args.get<std::string>("-raw");
+        if (!raw.empty()) fltr.saveRaw(raw);
         const double outSum = fltr.computeCheckSum("output");
         std::cout << " times min/max/avg: " << walltime << '/' << walltime << '/' << walltime << " [seconds]\n";
         std::cout << "Check sum: " << outSum << '\n';

@@ -101,6 +101,7 @@ _SIGS = {
     "fdb_stencil_sumsq": (i32, [vp, i32, p_dbl]),
     "fdb_stencil_get": (i32, [vp, i32, vp, i32]),
     "fdb_stencil_get_slab": (i32, [vp, i32, vp]),
+    "fdb_stencil_set_ref_wrap": (i32, [vp, i32]),
     "fdb_stencil_set_kernel": (i32, [vp, i32]),
     "fdb_stencil_get_kernel": (i32, [vp, p_i32]),
     "fdb_stencil_set_fuse": (i32, [vp, i32]),

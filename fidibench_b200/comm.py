@@ -48,8 +48,9 @@ class Comm:
         return float(v.value)
 
     def close(self) -> None:
+        """Destroy the communicator; engine handles created on it must have been closed first (FDB_E_STATE)."""
         if self._h:
-            lib.fdb_comm_destroy(self._h)
+            check(lib.fdb_comm_destroy(self._h))
             self._h = C.c_void_p()
 
     def __del__(self):

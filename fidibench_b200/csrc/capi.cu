@@ -49,6 +49,16 @@ struct UpwindSweep : SweepLauncher {
   }
   // the TMA kernels can mirror their top planes into the next slab's ghost planes themselves
   bool can_push(const Field*, int) const override { return tma; }
+  uint64_t key() const override {
+    uint64_t h = tma ? 0x51ull : 0x77ull;
+    for (int a = 0; a < 3; ++a) {
+      uint64_t bits;
+      memcpy(&bits, &k.c[a], sizeof(bits));
+      h = (h ^ bits) * 0x100000001B3ull;
+      h = (h ^ (uint64_t)(k.up[a] + 2) ^ ((uint64_t)k.active[a] << 8)) * 0x100000001B3ull;
+    }
+    return h | 1ull;
+  }
   int launch_push(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s, double* peer_out,
                   int64_t peer_from) override {
     if (!tma) return FDB_E_STATE;
@@ -61,6 +71,9 @@ struct StencilSweep : SweepLauncher {
   const StencilBranches* b = nullptr;
   bool fast = false;
   int fused_depth = 0;  // sweeps of this ghost depth run the two-applies-per-sweep kernel (0 = never)
+  uint64_t key() const override {  // the branches live in the handle and never change after creation
+    return (0xF17ull * 0x100000001B3ull) ^ ((uint64_t)fast << 1) ^ ((uint64_t)fused_depth << 4) ^ ((uint64_t)b->ref_wrap << 9) | 1ull;
+  }
   int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) override {
     if (fused_depth > 0 && depth == fused_depth) return launch_stencil_lap7_fused(*f, d, X, ibeg, iend, *b, s);
     return fast ? launch_stencil_lap7(*f, d, X, ibeg, iend, *b, s)
@@ -254,6 +267,10 @@ int stencil_common_create(int ndims, const int64_t* dims, int nbranch, const int
   }
   int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/2);
   if (rc == FDB_OK) rc = field_sync(&h->field);
+  if (rc == FDB_OK) {  // FDB_REF_WRAP=1: handles start in the reference-wrap compatibility mode where it applies
+    const char* rw = getenv("FDB_REF_WRAP");
+    if (rw && *rw && atoi(rw) != 0 && h->field.single()) h->br.ref_wrap = true;
+  }
   if (rc != FDB_OK) {
     field_destroy(&h->field);
     delete h;
@@ -392,6 +409,9 @@ int fdb_comm_barrier(fdb_comm* c) {
 
 int fdb_comm_destroy(fdb_comm* c) {
   if (!c) return FDB_OK;
+  if (c->users > 0)
+    return set_error(FDB_E_STATE, "%d engine handle(s) still use this communicator: destroy them first (their teardown "
+                     "is a collective over it)", c->users);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl) ncclCommDestroy(c->nccl);
@@ -477,7 +497,7 @@ int fdb_upwind_default_dt(const fdb_upwind* h, double* dt) {
   double best = DBL_MAX;
   for (int j = 0; j < h->field.geo.ndims; ++j) {
     const double dx = h->lengths[j] / (double)(size_t)h->num_cells[j];
-    const double val = courant * dx / h->velocity[j];
+    const double val = courant * dx / fabs(h->velocity[j]);  // |v|: bit-identical for the reference's v > 0
     best = (val < best ? val : best);
   }
   *dt = best;
@@ -754,9 +774,18 @@ int fdb_stencil_set_input_separable(fdb_stencil* h, const double* const* factors
   FDB_GUARD_END
 }
 
+int fdb_stencil_set_ref_wrap(fdb_stencil* h, int on) {
+  if (!h) return set_error(FDB_E_INVALID, "null handle");
+  if (on && !h->field.single())
+    return set_error(FDB_E_STATE, "the reference's wrap is only reproduced on a single slab (its off-rank indices go "
+                     "through MPI windows, not through the modulo)");
+  h->br.ref_wrap = on != 0;
+  return FDB_OK;
+}
+
 int fdb_stencil_get_kernel(const fdb_stencil* h, int* kernel) {
   if (!h || !kernel) return set_error(FDB_E_INVALID, "null argument");
-  const bool can = stencil_lap7_supported(h->field, h->br);
+  const bool can = !h->br.ref_wrap && stencil_lap7_supported(h->field, h->br);
   *kernel = (h->kernel == FDB_KERNEL_GENERIC || !can) ? FDB_KERNEL_GENERIC : FDB_KERNEL_TMA;
   return FDB_OK;
 }
@@ -765,7 +794,7 @@ int fdb_stencil_set_kernel(fdb_stencil* h, int kernel) {
   if (!h) return set_error(FDB_E_INVALID, "null handle");
   if (kernel != FDB_KERNEL_AUTO && kernel != FDB_KERNEL_GENERIC && kernel != FDB_KERNEL_TMA)
     return set_error(FDB_E_INVALID, "unknown kernel id %d", kernel);
-  if (kernel == FDB_KERNEL_TMA && !stencil_lap7_supported(h->field, h->br))
+  if (kernel == FDB_KERNEL_TMA && (h->br.ref_wrap || !stencil_lap7_supported(h->field, h->br)))
     return set_error(FDB_E_INVALID, "the TMA kernel only runs the 3-D 7-point stencil with an even last extent");
   h->kernel = kernel;
   return FDB_OK;

@@ -75,6 +75,7 @@ struct fdb_comm {
   cudaStream_t stream = nullptr;  // small collectives (checksum gather, barrier)
   double* scratch = nullptr;      // device scratch for those collectives
   size_t scratch_doubles = 0;
+  int users = 0;                  // engine handles created on this communicator and not yet destroyed
 };
 
 namespace fdb {
@@ -139,6 +140,10 @@ struct Field {
   int ghost_depth[2] = {0, 0};     // how many ghost planes (nearest the body) that exchange refreshed
   bool ghosts_valid = false;
   double last_ms = 0, last_updates = 0, last_halo_bytes = 0;
+  // CUDA graphs of whole sweep plans on single-slab fields (launch-bound grids), keyed by launcher + parity + depths
+  struct PlanGraph { uint64_t key; cudaGraphExec_t exec; int launches; };
+  std::vector<PlanGraph> plan_graphs;
+  cudaStream_t s_capture = nullptr;
 
   double* body(int d, int p) const { return slabs[d].buf[p] + (int64_t)G * geo.plane(); }
   double* ghost_lo(int d, int p) const;  // G planes below local plane 0 (never null)
@@ -188,6 +193,9 @@ struct SweepLauncher {
     return FDB_E_STATE;
   }
   virtual bool can_push(const Field*, int /*depth*/) const { return false; }
+  // Everything the launches bake in besides (field, parity, depths): two launchers with the same non-zero key
+  // enqueue identical kernels, so a captured CUDA graph of a sweep plan can be replayed.  0 = do not cache.
+  virtual uint64_t key() const { return 0; }
   virtual ~SweepLauncher() {}
 };
 // runs the sweeps depths[0..n) back to back (each advances the field once; cur flips after
@@ -216,6 +224,7 @@ struct StencilBranches {
   int nbranch = 0;
   int off[32][3];   // internal-axis offsets, already in application order
   double w[32];
+  bool ref_wrap = false;  // the reference's non-periodic wrap for extents that do not divide 2^64 (generic kernel)
 };
 int launch_stencil_generic(const Field& f, int d, int X, int64_t ibeg, int64_t iend,
                            const StencilBranches& b, cudaStream_t s);

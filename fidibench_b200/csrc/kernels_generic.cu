@@ -74,6 +74,7 @@ struct StencilArgs {
   int64_t nloc, n1, n2, ibeg, iend;
   int G;
   int nbranch;
+  int ref_wrap;  // reproduce Filter.cpp:240's (int %= size_t) wrap instead of the periodic one (single slab only)
   int off[32][3];
   double w[32];
 };
@@ -81,6 +82,15 @@ struct StencilArgs {
 __device__ __forceinline__ int64_t wrap(int64_t v, int64_t n) {
   v %= n;
   return v < 0 ? v + n : v;
+}
+
+// ref: Filter.cpp:237-240 -- `indOffset[j] = inds[j] + offset[j]` is an int, `indOffset[j] %= globalDims[j]`
+// converts it to size_t first: -1 becomes (2^64 - 1) mod n, which is n - 1 only when n divides 2^64
+// (SURVEY.md H2).  Opt-in compatibility mode, see fdb_stencil_set_ref_wrap.
+__device__ __forceinline__ int64_t wrap_ref(int64_t ind, int off, int64_t n) {
+  const int v = (int)ind + off;
+  const unsigned long long u = (unsigned long long)(long long)v;
+  return (int64_t)(int)(u % (unsigned long long)n);
 }
 
 // ref: Filter::applyFilter, cxx/Filter.cpp:191-263.  acc starts at 0.0 and takes
@@ -97,9 +107,10 @@ __global__ void __launch_bounds__(kThreads) stencil_generic_kernel(StencilArgs a
     double acc = 0.0;
     for (int b = 0; b < a.nbranch; ++b) {
       // axis 0 is not wrapped here: planes outside [0,nloc) live in the ghosts
-      const double* p = plane_ptr(a.body, a.glo, a.ghi, i + a.off[b][0], a.nloc, a.G, plane);
-      const int64_t jj = wrap(j + a.off[b][1], a.n1);
-      const int64_t kk = wrap(k + a.off[b][2], a.n2);
+      const double* p = a.ref_wrap ? a.body + wrap_ref(i, a.off[b][0], a.nloc) * plane
+                                   : plane_ptr(a.body, a.glo, a.ghi, i + a.off[b][0], a.nloc, a.G, plane);
+      const int64_t jj = a.ref_wrap ? wrap_ref(j, a.off[b][1], a.n1) : wrap(j + a.off[b][1], a.n1);
+      const int64_t kk = a.ref_wrap ? wrap_ref(k, a.off[b][2], a.n2) : wrap(k + a.off[b][2], a.n2);
       acc = __dadd_rn(acc, __dmul_rn(a.w[b], p[jj * a.n2 + kk]));
     }
     a.out[i * plane + r] = acc;
@@ -294,6 +305,7 @@ int launch_stencil_generic(const Field& f, int d, int X, int64_t ibeg, int64_t i
   a.iend = iend;
   a.G = f.G;
   a.nbranch = b.nbranch;
+  a.ref_wrap = (b.ref_wrap && f.single()) ? 1 : 0;
   for (int i = 0; i < b.nbranch; ++i) {
     a.off[i][0] = b.off[i][0]; a.off[i][1] = b.off[i][1]; a.off[i][2] = b.off[i][2];
     a.w[i] = b.w[i];

@@ -145,23 +145,42 @@ static int field_open_neighbours_ipc(Field* f) {
   Slab& s = f->slabs[0];
   fdb_comm* c = f->comm;
   const int n = c->nranks;
-  struct Pack { cudaIpcMemHandle_t h[3]; };
+  struct Pack { cudaIpcMemHandle_t h[3]; double ok; };
   static_assert(sizeof(Pack) % sizeof(double) == 0, "pack size");
   const size_t words = sizeof(Pack) / sizeof(double);
+  // Every rank runs the SAME sequence of collectives whatever fails locally (a rank that skipped the
+  // all-gather would leave the others hanging in it): local failures travel inside the pack.
   Pack mine;
-  FDB_CUDA(cudaIpcGetMemHandle(&mine.h[0], s.buf[0]));
-  FDB_CUDA(cudaIpcGetMemHandle(&mine.h[1], s.buf[1]));
-  FDB_CUDA(cudaIpcGetMemHandle(&mine.h[2], s.flags));
-  double *dsend = nullptr, *drecv = nullptr;
-  FDB_CUDA(cudaMalloc(&dsend, sizeof(Pack)));
-  FDB_CUDA(cudaMalloc(&drecv, sizeof(Pack) * (size_t)n));
-  FDB_CUDA(cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice));
-  FDB_NCCL(ncclAllGather(dsend, drecv, words, ncclDouble, c->nccl, c->stream));
-  FDB_CUDA(cudaStreamSynchronize(c->stream));
+  memset(&mine, 0, sizeof(mine));
+  int local = FDB_OK;
+  {
+    cudaError_t e = cudaIpcGetMemHandle(&mine.h[0], s.buf[0]);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.h[1], s.buf[1]);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.h[2], s.flags);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      local = set_error(FDB_E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+  }
+  mine.ok = (local == FDB_OK) ? 1.0 : 0.0;
   std::vector<Pack> all((size_t)n);
-  FDB_CUDA(cudaMemcpy(all.data(), drecv, sizeof(Pack) * (size_t)n, cudaMemcpyDeviceToHost));
-  cudaFree(dsend);
-  cudaFree(drecv);
+  double *dsend = nullptr, *drecv = nullptr;
+  auto gather = [&]() -> int {
+    FDB_CUDA(cudaMalloc(&dsend, sizeof(Pack)));
+    FDB_CUDA(cudaMalloc(&drecv, sizeof(Pack) * (size_t)n));
+    FDB_CUDA(cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice));
+    FDB_NCCL(ncclAllGather(dsend, drecv, words, ncclDouble, c->nccl, c->stream));
+    FDB_CUDA(cudaStreamSynchronize(c->stream));
+    FDB_CUDA(cudaMemcpy(all.data(), drecv, sizeof(Pack) * (size_t)n, cudaMemcpyDeviceToHost));
+    return FDB_OK;
+  };
+  const int grc = gather();
+  if (dsend) cudaFree(dsend);
+  if (drecv) cudaFree(drecv);
+  FDB_TRY(grc);
+  if (local != FDB_OK) return local;
+  for (int r = 0; r < n; ++r)
+    if (all[(size_t)r].ok != 1.0) return set_error(FDB_E_CUDA, "rank %d could not export its buffers over CUDA IPC", r);
   const int prev = (c->rank + n - 1) % n, next = (c->rank + 1) % n;
   int opened = 0;
   auto open3 = [&](int rank, int side) -> int {
@@ -217,6 +236,7 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
   f->comm = comm;
   f->cur = 0;
   if (comm) {
+    ++comm->users;  // fdb_comm_destroy refuses while handles still use the communicator
     f->ngpus = 1;
     f->nparts = comm->nranks;
   } else {
@@ -271,20 +291,26 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
     FDB_CUDA(cudaEventRecord(s.ev_ghost_ready[1], s.s_bnd));
     FDB_CUDA(cudaEventRecord(s.ev_xchg_done, s.s_bnd));
   }
-  // peer access between neighbouring devices of this process
+  // peer access between neighbouring devices of this process.  The direct transport (raw neighbour
+  // pointers, kernel peer stores, stream memory operations on the neighbour's counters) needs it on
+  // EVERY neighbour pair; without it the event-ordered cudaMemcpyPeerAsync transport is used, which
+  // stages through the host when it has to.  FDB_NO_PEER=1 pretends there is none (tests).
+  bool all_peer = true;
   if (!comm && f->ngpus > 1) {
+    const char* np = getenv("FDB_NO_PEER");
+    const bool pretend_none = np && *np && atoi(np) != 0;
     for (int d = 0; d < f->ngpus; ++d) {
       FDB_CUDA(cudaSetDevice(f->slabs[d].device));
       for (int o : {(d + 1) % f->ngpus, (d + f->ngpus - 1) % f->ngpus}) {
         if (o == d) continue;
         int can = 0;
         FDB_CUDA(cudaDeviceCanAccessPeer(&can, f->slabs[d].device, f->slabs[o].device));
-        if (can) {
+        if (can && !pretend_none) {
           cudaError_t pe = cudaDeviceEnablePeerAccess(f->slabs[o].device, 0);
-          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
-            return set_error(FDB_E_CUDA, "cudaDeviceEnablePeerAccess(%d->%d): %s", d, o,
-                             cudaGetErrorString(pe));
+          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) all_peer = false;
           (void)cudaGetLastError();
+        } else {
+          all_peer = false;
         }
       }
     }
@@ -293,6 +319,7 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
   const char* halo_env = getenv("FDB_HALO");
   f->direct = !(halo_env && strcmp(halo_env, "nccl") == 0) && stream_memops_available();
   f->push_stores = !(halo_env && strcmp(halo_env, "copy") == 0);  // FDB_HALO=copy: copy engines only
+  if (!all_peer) { f->direct = false; f->push_stores = false; }
   if (f->nparts > 1 && f->direct) {
     if (comm) {
       int rc = field_open_neighbours_ipc(f);
@@ -349,6 +376,13 @@ void field_destroy(Field* f) {
       if (ev) cudaEventDestroy(ev);
   }
   f->slabs.clear();
+  for (auto& g : f->plan_graphs) cudaGraphExecDestroy(g.exec);
+  f->plan_graphs.clear();
+  if (f->s_capture) { cudaStreamDestroy(f->s_capture); f->s_capture = nullptr; }
+  if (f->comm) {
+    --f->comm->users;
+    f->comm = nullptr;
+  }
   (void)cudaGetLastError();
 }
 
@@ -706,6 +740,54 @@ int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n) {
   if (f->single()) {
     Slab& s = f->slabs[0];
     FDB_CUDA(cudaSetDevice(s.device));
+    // Launch-bound grids: a plan of several sweeps is captured once into a CUDA graph and
+    // replayed -- one launch call per advect()/iterate() instead of one per sweep.  Grids whose sweeps run for
+    // hundreds of microseconds gain nothing, so only small fields take this path (FDB_GRAPH=0 never, =1 always).
+    static const int graph_mode = [] { const char* g = getenv("FDB_GRAPH"); return (g && *g) ? atoi(g) : -1; }();
+    const bool want_graph = n >= 2 && L->key() != 0 &&
+                            (graph_mode > 0 || (graph_mode < 0 && f->geo.total() <= (int64_t)(1 << 24)));
+    if (want_graph) {
+      uint64_t key = L->key() * 0x9E3779B97F4A7C15ull + (uint64_t)f->cur;
+      // the launchers read their tuning knobs from the environment at every launch: part of what is baked in
+      for (const char* knob : {"FDB_FUSED_CFG", "FDB_TMA_CFG", "FDB_TMA_CI", "FDB_MAX_CTAS", "FDB_LAPF_CFG", "FDB_LAP_CFG",
+                               "FDB_LAPF_GENERAL", "FDB_FUSED_IMPL"}) {
+        const char* v = getenv(knob);
+        for (const char* c = (v ? v : ""); *c; ++c) key = (key ^ (uint64_t)(unsigned char)*c) * 0x100000001B3ull;
+        key = (key ^ 0xFFull) * 0x100000001B3ull;
+      }
+      for (int i = 0; i < n; ++i) key = (key ^ (uint64_t)depths[i]) * 0x100000001B3ull;
+      key ^= (uint64_t)n << 56;
+      Field::PlanGraph* hit = nullptr;
+      for (auto& g : f->plan_graphs)
+        if (g.key == key) hit = &g;
+      if (!hit) {
+        if (!f->s_capture) FDB_CUDA(cudaStreamCreateWithFlags(&f->s_capture, cudaStreamNonBlocking));
+        const int64_t before = launch_count();
+        FDB_CUDA(cudaStreamBeginCapture(f->s_capture, cudaStreamCaptureModeRelaxed));  // first-use setup calls are not stream work
+        int rc = FDB_OK, X = f->cur;
+        for (int i = 0; i < n && rc == FDB_OK; ++i, X = 1 - X) rc = L->launch(f, 0, X, depths[i], 0, s.nloc(), f->s_capture);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(f->s_capture, &graph);
+        const int launches = (int)(launch_count() - before);
+        count_launch(-launches);  // captured, not launched
+        if (rc != FDB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return set_error(FDB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return set_error(FDB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        if (f->plan_graphs.size() >= 16) {  // plans vary with (steps, dt): keep the cache small
+          cudaGraphExecDestroy(f->plan_graphs.front().exec);
+          f->plan_graphs.erase(f->plan_graphs.begin());
+        }
+        f->plan_graphs.push_back({key, exec, launches});
+        hit = &f->plan_graphs.back();
+      }
+      FDB_CUDA(cudaGraphLaunch(hit->exec, s.s_main));
+      count_launch(hit->launches);
+      f->cur = (f->cur + n) & 1;
+      return FDB_OK;
+    }
     for (int i = 0; i < n; ++i) {
       FDB_TRY(L->launch(f, 0, f->cur, depths[i], 0, s.nloc(), s.s_main));
       f->cur = 1 - f->cur;

@@ -185,6 +185,10 @@ class Filter:
         check(lib.fdb_stencil_get(self._h, which, out.ctypes.data_as(C.c_void_p), layout))
         return out
 
+    def set_ref_wrap(self, on: bool) -> None:
+        """Reproduce Filter.cpp:240's (int %= size_t) wrap (non-periodic unless the extent is a power of two)."""
+        check(lib.fdb_stencil_set_ref_wrap(self._h, 1 if on else 0))
+
     def set_kernel(self, kernel: int) -> None:
         check(lib.fdb_stencil_set_kernel(self._h, int(kernel)))
 

@@ -94,6 +94,8 @@ int fdb_comm_rank(const fdb_comm *c, int *rank, int *nranks);
 int fdb_comm_barrier(fdb_comm *c);
 /* max over ranks of a host double (timing), collective */
 int fdb_comm_max(fdb_comm *c, double *value);
+/* FDB_E_STATE while engine handles created on the communicator still exist: destroy those first (on every
+ * rank, in the same order -- their teardown is a collective) */
 int fdb_comm_destroy(fdb_comm *c);
 
 /* ---- Upwind engine -------------------------------------------------------- */
@@ -132,7 +134,8 @@ int fdb_upwind_advect(fdb_upwind *h, int64_t numTimeSteps, double deltaTime);
 /* enqueue only; pair with fdb_upwind_sync */
 int fdb_upwind_advect_async(fdb_upwind *h, int64_t numTimeSteps, double deltaTime);
 int fdb_upwind_sync(fdb_upwind *h);
-/* ref: main()'s dt = min_j 0.1*dx_j/v_j, upwind.cxx:186-192 */
+/* ref: main()'s dt = min_j 0.1*dx_j/v_j, upwind.cxx:186-192, with |v_j| so that the negative velocities the
+ * class supports still give a positive, stable step (identical bits for the reference's v > 0) */
 int fdb_upwind_default_dt(const fdb_upwind *h, double *dt);
 
 /* ref: Upwind::checksum(), upwind.cxx:91-93 (collective in dist mode; every rank gets the sum) */
@@ -211,6 +214,13 @@ int fdb_stencil_checksum(fdb_stencil *h, int which, double *sum);
 int fdb_stencil_sumsq(fdb_stencil *h, int which, double *sumsq);
 int fdb_stencil_get(fdb_stencil *h, int which, double *host_field, int layout);
 int fdb_stencil_get_slab(fdb_stencil *h, int which, double *host_slab);
+/* Compatibility with the reference's index wrap.  Filter.cpp:237-240 reduces `int(index) + offset` with
+ * `%= size_t(extent)`: a negative index is converted to size_t first, so -1 wraps to (2^64 - 1) mod N -- the
+ * periodic N - 1 only when N is a power of two (for the reference's default `laplacian -numCells 8000`, 7615).
+ * This library wraps periodically by default; on = 1 reproduces the reference's arithmetic bit for bit on a
+ * single-slab handle (generic kernel; FDB_E_STATE on several slabs).  Environment FDB_REF_WRAP=1 turns it on
+ * at creation. */
+int fdb_stencil_set_ref_wrap(fdb_stencil *h, int on);
 int fdb_stencil_set_kernel(fdb_stencil *h, int kernel);
 int fdb_stencil_get_kernel(const fdb_stencil *h, int *kernel);
 int fdb_stencil_set_stream(fdb_stencil *h, void *cuda_stream);

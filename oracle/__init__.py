@@ -235,6 +235,21 @@ class _Ref:
     def upwind_exe(self) -> str:
         return os.path.join(self.dir, "upwindCxx")
 
+    def run_main(self, which, argv, cwd):
+        """The reference's own laplacian.cxx / upwindMpi.cxx main() (untouched, single rank against the MPI stub),
+        run in a process of its own inside `cwd` (they write laplacian.vtk / upMpi.vtk there).
+        which: "laplacian" | "upwindmpi".  Returns the CompletedProcess (stdout = the driver's output)."""
+        import sys
+        code = (
+            "import ctypes, sys\n"
+            f"L = ctypes.CDLL({os.path.join(self.dir, 'libref_filter.so')!r})\n"
+            "argv = [b'ref'] + [a.encode() for a in sys.argv[1:]]\n"
+            "arr = (ctypes.c_char_p * (len(argv) + 1))(*argv, None)\n"
+            f"rc = L.fdb_ref_{which}_main(len(argv), arr)\n"
+            "sys.stdout.flush(); sys.exit(rc)\n")
+        return subprocess.run([sys.executable, "-c", code] + [str(a) for a in argv], cwd=cwd, capture_output=True,
+                              text=True, timeout=600)
+
 
 # --------------------------------------------------------------------------- #
 # numpy restatements

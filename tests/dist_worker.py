@@ -233,6 +233,15 @@ def gpu_main():
     assert np.array_equal(up.slab(), oracle.c.upwind_advect(a, 14)[up.lo:up.hi]), f"rank {rank}: repeated advect differs"
     up.close()
 
+    # the communicator refuses to go away under a live handle (its teardown is a collective over it)
+    up = fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, comm=comm)
+    try:
+        comm.close()
+        raise AssertionError("Comm.close() succeeded with a live engine handle")
+    except fb.FdbError as e:
+        assert e.code == -6
+    up.close()
+
     dist.barrier()
     print(f"RANK {rank} OK gpu", flush=True)
     comm.close()

@@ -6,8 +6,10 @@ import subprocess
 
 import pytest
 
+import numpy as np
+
 import oracle
-from conftest import ROOT
+from conftest import ROOT, SEED
 
 
 @pytest.fixture(scope="module")
@@ -118,3 +120,72 @@ def test_stencil2d_driver_prints_the_reference_values(drivers, gpu_fb):
     f = lambda i, j: 1.0 if (i % 8) * (j % 8) == 0 else 0.0
     for (i, j), v in vals.items():
         assert v == f(i + 1, j) - f(i, j - 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built on this machine")
+@pytest.mark.parametrize("flags", [("-numDims", "3", "-numCells", "8"), ("-numDims", "2", "-numCells", "16"),
+                                   ("-numDims", "2", "-numCells", "12", "-refwrap")])
+def test_laplacian_driver_vtk_is_byte_identical_to_the_reference(drivers, gpu_fb, tmp_path, flags):
+    """SURVEY.md 8(f3): Filter::saveVTK (Filter.cpp:487-538 + cxx/writeVTK.cpp:12-95) through the untouched
+    laplacian.cxx main() against drivers/Filter.hpp::saveVTK through laplacianCuda, same flags.  12 is not a power
+    of two: there the reference's index wrap is not periodic (H2) and -refwrap reproduces it."""
+    ours_dir, ref_dir = tmp_path / "ours", tmp_path / "ref"
+    ours_dir.mkdir(); ref_dir.mkdir()
+    ref_flags = [f for f in flags if f != "-refwrap"]
+    q = oracle.ref().run_main("laplacian", list(ref_flags) + ["-vtk"], ref_dir)
+    assert q.returncode == 0, q.stderr
+    p = subprocess.run([drivers["laplacianCuda"], *flags, "-vtk", "-raw", "out.bin"], cwd=ours_dir, capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert (ours_dir / "laplacian.vtk").read_bytes() == (ref_dir / "laplacian.vtk").read_bytes()
+    # the lines both drivers print
+    for key in ("global dimensions:", "Check sums:", "Data will be written to file laplacian.vtk"):
+        ours = [l for l in p.stdout.splitlines() if key in l]
+        ref = [l for l in q.stdout.splitlines() if key in l]
+        assert ours and len(ours) == len(ref)
+    # the raw dump carries the same field at full precision
+    nd, n = int(flags[1]), int(flags[3])
+    raw = np.fromfile(ours_dir / "out.bin", dtype=np.float64).reshape((n,) * nd)
+    off, w = oracle.laplacian_stencil(nd)
+    r = oracle.c.laplacian_input((n,) * nd)
+    for _ in range(10):
+        r = oracle.c.stencil_apply(r, off, w, ref_wrap_quirk="-refwrap" in flags)
+    assert np.array_equal(raw, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built on this machine")
+def test_upwindmpi_driver_vtk_and_stdout_match_the_reference(drivers, gpu_fb, tmp_path):
+    ours_dir, ref_dir = tmp_path / "ours", tmp_path / "ref"
+    ours_dir.mkdir(); ref_dir.mkdir()
+    flags = ["-numCells", "8", "-numSteps", "3", "-vtk"]
+    q = oracle.ref().run_main("upwindmpi", flags, ref_dir)
+    assert q.returncode == 0, q.stderr
+    p = subprocess.run([drivers["upwindMpiCuda"], *flags, "-raw", "out.bin"], cwd=ours_dir, capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert (ours_dir / "upMpi.vtk").read_bytes() == (ref_dir / "upMpi.vtk").read_bytes()
+    keep = lambda out: [l for l in out.splitlines() if l.startswith("iter ") or l.startswith("Check sum:")]
+    assert keep(p.stdout) == keep(q.stdout) and len(keep(p.stdout)) == 4
+    assert np.fromfile(ours_dir / "out.bin", dtype=np.float64).size == 512
+
+
+@pytest.mark.gpu
+def test_upwind_driver_raw_dump_and_anisotropic_flags(drivers, gpu_fb, tmp_path):
+    """-raw round trip at full precision; -nx/-ny/-nz/-lx/-ly/-lz expose what the class supports and the reference's
+    main() does not (upwind.cxx:174,182-183)."""
+    p = subprocess.run([drivers["upwindCuda"], "-numCells", "16", "-numSteps", "7", "-raw", "f.bin"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    f0 = np.zeros((16, 16, 16)); f0.reshape(-1)[0] = 1.0
+    assert np.array_equal(np.fromfile(tmp_path / "f.bin", dtype=np.float64).reshape(16, 16, 16), oracle.c.upwind_advect(f0, 7))
+    p = subprocess.run([drivers["upwindCuda"], "-nx", "12", "-ny", "20", "-nz", "36", "-lx", "1.5", "-lz", "0.75", "-vy", "-2",
+                        "-numSteps", "5", "-raw", "g.bin"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "number of cells:  12 20 36\n" in p.stdout
+    shape, vel, lens = (12, 20, 36), [1.0, -2.0, 1.0], [1.5, 1.0, 0.75]
+    g0 = np.zeros(shape); g0.reshape(-1)[0] = 1.0
+    dt = oracle.c.upwind_dt(shape, [abs(v) for v in vel], lens)
+    ref = oracle.c.upwind_advect(g0, 5, velocity=vel, lengths=lens, dt=dt)
+    assert np.array_equal(np.fromfile(tmp_path / "g.bin", dtype=np.float64).reshape(shape), ref)

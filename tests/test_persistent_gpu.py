@@ -141,3 +141,34 @@ def test_laplacian_fused_run_to_run_determinism_512_cubed(gpu_fb):
             fl.iterate(4)
             got.append(digest(fl.get()))
     assert got[0] == got[1]
+
+
+def test_cuda_graph_replay_of_small_plans_is_bitwise_and_counts_launches(gpu_fb):
+    """Launch-bound grids replay a captured CUDA graph of the whole sweep plan (runtime.cu: field_run_sweeps)."""
+    rng = np.random.default_rng(SEED + 230)
+    a = rng.random((32, 40, 64))
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as up:
+        up.set_field(a)
+        dt = up.default_dt()
+        n0 = gpu_fb.launch_count()
+        for _ in range(3):                 # same plan three times: one capture, then replays
+            up.advect(10, dt)
+        per_call = (gpu_fb.launch_count() - n0) // 3
+        assert per_call == 4               # [3, 3, 2, 2]
+        up.advect(7, dt)                   # another plan, odd parity start
+        up.advect(10, 0.5 * dt)            # same depths, other coefficients: must not replay the old graph
+        out = up.field()
+    ref = C.upwind_advect(a, 37, dt=dt)
+    ref = C.upwind_advect(ref, 10, dt=0.5 * dt)
+    assert np.array_equal(out, ref)
+    off, w, st = lap7()
+    b = rng.random((16, 32, 128)) - 0.5
+    with gpu_fb.Filter(b.shape, [0.0] * 3, [1.0] * 3, st) as fl:
+        fl.set_input(b)
+        fl.iterate(4)
+        fl.iterate(4)
+        fl.iterate(3)
+        r = b
+        for _ in range(11):
+            r = C.stencil_apply(r, off, w)
+        assert np.array_equal(fl.get(), r)

@@ -333,3 +333,82 @@ def test_fused_two_applies_in_process_slabs(gpu_fb, ngpus):
         out12 = fl.get()
     assert np.array_equal(out, _applies(a, off, w, 11))
     assert np.array_equal(out12, _applies(a, off, w, 12))
+
+
+@pytest.mark.parametrize("shape", [(24, 24), (10, 12, 14), (30,), (48, 20, 36)])
+def test_reference_wrap_compatibility_mode(gpu_fb, shape):
+    """Filter.cpp:240 wraps with (int %= size_t): not periodic unless the extent is a power of two.
+    Default = true periodic wrap (pinned against the oracle without the quirk); set_ref_wrap(True) reproduces the
+    reference bit for bit (oracle quirk mode == oracle/_ref, tests/test_oracle.py) and runs the generic kernel."""
+    nd = len(shape)
+    off, w = oracle.laplacian_stencil(nd)
+    st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
+    a = np.random.default_rng(SEED + 40).random(shape)
+    with gpu_fb.Filter(shape, [0.0] * nd, [1.0] * nd, st) as fl:
+        fl.set_input(a)
+        fl.applyFilter()
+        periodic = fl.get()
+        assert np.array_equal(periodic, C.stencil_apply(a, off, w, ref_wrap_quirk=False))
+        fl.set_ref_wrap(True)
+        assert fl.kernel() == gpu_fb.FDB_KERNEL_GENERIC
+        fl.set_input(a)
+        fl.applyFilter()
+        quirk = fl.get()
+        assert np.array_equal(quirk, C.stencil_apply(a, off, w, ref_wrap_quirk=True))
+        assert not np.array_equal(quirk, periodic)     # none of these extents divides 2^64
+        fl.set_ref_wrap(False)
+        fl.set_input(a)
+        fl.iterate(2)
+        assert np.array_equal(fl.get(), C.stencil_apply(periodic, off, w))
+
+
+def test_reference_wrap_reproduces_the_reference_golden_on_24x24(gpu_fb):
+    g = golden("laplacian2d_32.npz")
+    off, w = oracle.laplacian_stencil(2)
+    st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
+    with gpu_fb.Filter((24, 24), [0.0] * 2, [1.0] * 2, st) as fl:
+        fl.set_ref_wrap(True)
+        fl.set_input_separable(fl.laplacian_factors())
+        assert np.array_equal(fl.get(gpu_fb.FDB_INPUT), g["input24"])
+        fl.applyFilter()
+        assert np.array_equal(fl.get(), g["out24_quirk"])   # what the untouched Filter.cpp produced
+
+
+def test_reference_wrap_is_refused_on_several_slabs_and_filter_slab_is_validated(gpu_fb):
+    off, w = oracle.laplacian_stencil(3)
+    st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
+    with gpu_fb.Filter((8, 8, 8), [0.0] * 3, [1.0] * 3, st) as fl:
+        with pytest.raises(ValueError):
+            fl.set_input_slab(np.zeros((4, 8, 8)))      # ADVICE r1: a short slab must not reach cudaMemcpy
+        assert fl.getNumProcs() == 1
+    if gpu_fb.device_count() >= 2:
+        with gpu_fb.Filter((8, 8, 8), [0.0] * 3, [1.0] * 3, st, ngpus=2) as fl:
+            assert fl.getNumProcs() == 2
+            with pytest.raises(gpu_fb.FdbError) as e:
+                fl.set_ref_wrap(True)
+            assert e.value.code == -6
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_in_process_slabs_without_peer_access_take_the_copy_transport(gpu_fb, ngpus, monkeypatch):
+    """when a neighbour pair has no peer access the direct transport (raw peer pointers, peer
+    stores, stream memory operations) must not be taken; FDB_NO_PEER=1 pretends there is none."""
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    monkeypatch.setenv("FDB_NO_PEER", "1")
+    rng = np.random.default_rng(SEED + 41)
+    a = rng.random((8 * ngpus, 24, 64))
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, ngpus=ngpus) as up:
+        up.set_field(a)
+        up.advect(8 * ngpus + 3, up.default_dt())
+        assert np.array_equal(up.field(), C.upwind_advect(a, 8 * ngpus + 3))
+    off, w = oracle.laplacian_stencil(3)
+    st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
+    b = rng.random((4 * ngpus, 16, 128)) - 0.5
+    with gpu_fb.Filter(b.shape, [0.0] * 3, [1.0] * 3, st, ngpus=ngpus) as fl:
+        fl.set_input(b)
+        fl.iterate(5)
+        ref = b
+        for _ in range(5):
+            ref = C.stencil_apply(ref, off, w)
+        assert np.array_equal(fl.get(), ref)

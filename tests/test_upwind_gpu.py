@@ -326,3 +326,20 @@ def test_negative_velocities_run_the_tiled_kernels_on_a_mirrored_grid(gpu_fb, ve
         assert np.array_equal(up.field(), delta(shape))
         up.advect(5, dt)
         assert np.array_equal(up.field(), C.upwind_advect(delta(shape), 5, velocity=vel, lengths=lengths, dt=dt))
+
+
+def test_default_dt_is_positive_for_negative_velocities(gpu_fb):
+    """the ABI helper uses |v| like drivers/upwindCuda.cxx (same bits as the reference for v > 0)."""
+    rng = np.random.default_rng(SEED + 50)
+    a = rng.random((6, 10, 36))
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as up:
+        assert up.default_dt() == C.upwind_dt(a.shape, [1.0] * 3, [1.0] * 3)
+    vel = [-1.0, 2.0, -0.5]
+    with gpu_fb.Upwind(vel, [1.0] * 3, a.shape) as up:
+        dt = up.default_dt()
+        assert dt > 0 and dt == C.upwind_dt(a.shape, [abs(v) for v in vel], [1.0] * 3)
+        up.set_field(a)
+        up.advect(6, dt)
+        out = up.field()
+    assert np.array_equal(out, C.upwind_advect(a, 6, velocity=vel, dt=dt))
+    assert abs(out).max() <= abs(a).max()   # a stable (monotone) step, not an anti-diffusive one
