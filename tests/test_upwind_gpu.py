@@ -198,8 +198,9 @@ def test_in_process_slabs_match_single_domain_oracle(gpu_fb, ngpus, kernel):
     f1, cs1, _, _ = run_gpu(gpu_fb, a, 20, kernel=k, ngpus=1)
     assert cs == cs1  # the reduction is bitwise partition-invariant
     # negative axis-0 velocity: the ghost plane sits above the slab
-    f, _, _, _ = run_gpu(gpu_fb, a, 9, velocity=[-1, 1, 1], ngpus=ngpus)
-    assert np.array_equal(f, C.upwind_advect(a, 9, velocity=[-1, 1, 1]))
+    dt = C.upwind_dt(a.shape, [1.0] * 3, [1.0] * 3)   # |v|: the reference's signed formula would give dt < 0
+    f, _, _, _ = run_gpu(gpu_fb, a, 9, velocity=[-1, 1, 1], dt=dt, ngpus=ngpus)
+    assert np.array_equal(f, C.upwind_advect(a, 9, velocity=[-1, 1, 1], dt=dt))
 
 
 def test_invalid_slab_count_is_a_decomposition_error(gpu_fb):
