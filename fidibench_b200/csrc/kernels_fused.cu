@@ -132,31 +132,12 @@ struct FusedCursor {
   }
 };
 
+// ---- loader warp (shared by both consumer formulations) --------------------------------------------
+// Lane 0 issues the TMA boxes of plane n; LAG planes later the warp waits for a plane to land, one lane per
+// stage row patches the periodic wrap columns of the first k-tile, and the stage is handed to the consumers.
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::MINB)
-    upwind3d_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
-  const uint32_t landed = xbuf + C::NX * C::X_BYTES;  // TMA bytes of the stage have arrived
-  const uint32_t full = landed + C::STAGES * 8;        // ... and its wrap columns are in place
-  const uint32_t empty = full + C::STAGES * 8;         // every consumer warp has read the stage
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(landed + 8 * s, 1);
-      mbar_init(full + 8 * s, 1);
-      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == C::CONSUMER_WARPS) {
-    // ===================== loader warp (see kernels_lapfused.cu) =====================
+__device__ __forceinline__ void fused_loader_warp(const FusedMaps& maps, const FusedArgs& a, uint32_t smem, uint32_t landed,
+                                                  uint32_t full, uint32_t empty, int lane) {
     if (lane == 0) {
 #pragma unroll
       for (int m = 0; m < 8; ++m) prefetch_tmap(&maps.m[m]);
@@ -214,6 +195,33 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
         --ahead;
       }
     }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+    upwind3d_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
+  const uint32_t landed = xbuf + C::NX * C::X_BYTES;  // TMA bytes of the stage have arrived
+  const uint32_t full = landed + C::STAGES * 8;        // ... and its wrap columns are in place
+  const uint32_t empty = full + C::STAGES * 8;         // every consumer warp has read the stage
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    fused_loader_warp<C>(maps, a, smem, landed, full, empty, lane);
     return;
   }
 
@@ -323,17 +331,194 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   }
 }
 
+// ---- second consumer formulation ("lean"): same tile pipeline, same arithmetic, fewer instructions --------
+// Measured on B200 (profiles/r02e_ubench_fp64_issue.txt): an FP64 instruction holds the issue port of its SM
+// sub-partition for two cycles and nothing else issues beside it, so the kernel's time is the SUM of
+// 2 x (FP64 instructions) + (everything else), and the first formulation spent 150 other instructions per 162
+// FP64 ones per warp and plane (44 of them register moves that shift plane i into the "plane i-1" registers).
+// Here
+//   * the plane loop is unrolled by two and the two register sets swap roles (previous plane / this plane):
+//     no moves;
+//   * plane counters are 32-bit, the stage/barrier addresses advance by constants, output rows are R pointers that
+//     advance by one plane, idle threads of the last warp duplicate thread 0 instead of being predicated off, and
+//     the peer stores of the halo push live in their own instantiation (PUSH).
+template <class C, bool PUSH>
+struct Lean {
+  static constexpr int T = C::T, R = C::R;
+  static constexpr uint32_t P = C::PITCH;
+
+  struct State {
+    uint32_t st;      // this thread's base inside the current stage
+    uint32_t bar;     // `full` barrier of the current stage (landed = bar - 8*STAGES, empty = bar + 8*STAGES)
+    uint32_t par;     // phase parity of the current round over the stages
+    uint32_t st0, bar0, bar_end;
+    uint32_t xt0, xt1;  // this thread's base inside the two exchange tiles
+    double c0, c1, c2;
+    double* orow[C::R];   // output rows of the plane being computed
+    double* prow[C::R];   // the same rows in the next slab's ghost planes (PUSH)
+    int64_t plane_elems;
+    uint32_t smask;       // rows x columns this thread stores
+    int lane;
+  };
+
+  // one plane: level 0 comes from the stage, level s+1 from level s of this plane (X) and of the previous one (Pv)
+  template <int PARITY>
+  static __device__ __forceinline__ void step(State& z, double2 (&Pv)[C::T][C::R], double2 (&X)[C::T][C::R], bool store,
+                                              bool push) {
+    mbar_wait(z.bar, z.par);
+    mbar_wait(z.bar - 8 * C::STAGES, z.par);  // already complete: orders this thread behind the TMA writes
+    double km[R];
+    double2 up = lds_v2(z.st);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      X[0][r] = lds_v2(z.st + (1 + r) * P);
+      km[r] = lds_f64(z.st + (1 + r) * P - 8);
+    }
+    __syncwarp();
+    if (z.lane == 0) mbar_arrive(z.bar + 8 * C::STAGES);
+    z.st += C::STAGE_BYTES;
+    z.bar += 8;
+    if (z.bar == z.bar_end) { z.st = z.st0; z.bar = z.bar0; z.par ^= 1; }
+    const uint32_t m = store ? z.smask : 0u;
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+      double2 out[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double2 jm = (r == 0) ? up : X[s][r - 1];
+        double2 n;
+        n.x = upwind_cell(X[s][r].x, Pv[s][r].x, jm.x, km[r], z.c0, z.c1, z.c2);
+        n.y = upwind_cell(X[s][r].y, Pv[s][r].y, jm.y, X[s][r].x, z.c0, z.c1, z.c2);
+        if (s == T - 1) out[r] = n; else X[s + 1][r] = n;
+      }
+      if (s == T - 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((m >> r) & 1u) {
+            st_global_v2(z.orow[r], out[r].x, out[r].y);
+            if (PUSH && push) st_global_v2(z.prow[r], out[r].x, out[r].y);
+          }
+          z.orow[r] += z.plane_elems;
+          if (PUSH) z.prow[r] += z.plane_elems;
+        }
+      } else {
+        // hand level s+1 of this plane to the neighbours; the tiles alternate with every exchange
+        const uint32_t xb = (((PARITY * (T - 1) + s) & 1) == 0) ? z.xt0 : z.xt1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) sts_v2(xb + (1 + r) * P, X[s + 1][r].x, X[s + 1][r].y);
+        named_bar_sync(1, C::CONSUMERS);
+        up = lds_v2(xb);
+#pragma unroll
+        for (int r = 0; r < R; ++r) km[r] = lds_f64(xb + (1 + r) * P - 8);
+      }
+    }
+  }
+};
+
+template <class C, bool PUSH>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+    upwind3d_fused_lean_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
+  const uint32_t landed = xbuf + C::NX * C::X_BYTES;
+  const uint32_t full = landed + C::STAGES * 8;
+  const uint32_t empty = full + C::STAGES * 8;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    fused_loader_warp<C>(maps, a, smem, landed, full, empty, lane);
+    return;
+  }
+
+  using L = Lean<C, PUSH>;
+  // threads past the tile repeat thread 0's work (same values to the same shared-memory cells) and store nothing
+  const bool worker = tid < C::WORKERS;
+  const int wid = worker ? tid : 0;
+  const int tx = wid % C::TX;
+  const int ty = wid / C::TX;
+  const int q0 = ty * C::R;
+  const uint32_t xt = q0 * C::PITCH + (C::LEFT + 2 * tx) * 8;
+  typename L::State z;
+  z.st0 = smem + xt + (C::HR - C::T) * C::PITCH;
+  z.bar0 = full;
+  z.bar_end = full + 8 * C::STAGES;
+  z.st = z.st0;
+  z.bar = z.bar0;
+  z.par = 0;
+  z.xt0 = xbuf + xt;
+  z.xt1 = xbuf + C::X_BYTES + xt;
+  z.c0 = a.c0; z.c1 = a.c1; z.c2 = a.c2;
+  z.plane_elems = a.n1 * a.n2;
+  z.lane = lane;
+  uint32_t rowmask = 0;
+#pragma unroll
+  for (int r = 0; r < C::R; ++r)
+    if (worker && q0 + r >= C::T - 1) rowmask |= 1u << r;
+
+  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    const int kt = (int)(w % a.nkt);
+    const int jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;
+    const int64_t j = (int64_t)jt * C::BJ - (C::T - 1) + q0;
+    z.smask = (2 * tx >= C::HKC && k < a.n2) ? rowmask : 0u;
+#pragma unroll
+    for (int r = 0; r < C::R; ++r) {
+      if (j + r >= a.n1) z.smask &= ~(1u << r);
+      // rows of plane i0 - T (the first warm-up plane: never dereferenced before plane i0)
+      z.orow[r] = a.out + ((i0 - C::T) * a.n1 + j + r) * a.n2 + k;
+      if (PUSH) z.prow[r] = a.peer_out + ((i0 - C::T - a.peer_from) * a.n1 + j + r) * a.n2 + k;
+    }
+    double2 A[C::T][C::R], B[C::T][C::R];  // levels 0..T-1 of the previous plane / of this plane, swapping roles
+#pragma unroll
+    for (int s = 0; s < C::T; ++s)
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) A[s][r] = B[s][r] = make_double2(0.0, 0.0);
+
+    // T warm-up planes below the chunk, then the chunk; `q` counts planes from i0 - T
+    const int np = (int)(i1 - i0) + C::T;
+    const int push_from = PUSH ? (int)(a.peer_from - (i0 - C::T)) : 0;
+    int q = 0;
+    for (; q + 2 <= np; q += 2) {
+      L::template step<0>(z, A, B, q >= C::T, q >= push_from);
+      L::template step<1>(z, B, A, q + 1 >= C::T, q + 1 >= push_from);
+    }
+    if (q < np) {
+      // odd plane count: one more plane in the even roles (the next item starts from zeroed sets anyway)
+      L::template step<0>(z, A, B, q >= C::T, q >= push_from);
+      // with an odd number of exchanges per plane the next item would write the exchange tile this plane just read
+      if ((C::T - 1) & 1) named_bar_sync(1, C::CONSUMERS);
+    }
+  }
+}
+
 // ---- configurations ---------------------------------------------------------------------
 typedef void (*FusedKernel)(const FusedMaps, const FusedArgs);
 struct FusedConfig {
   int T, CJ, BJ, BK, BKP, HR, threads, smem;
-  FusedKernel kernel;
+  FusedKernel kernel;                 // first consumer formulation (FDB_FUSED_IMPL=1)
+  FusedKernel lean, lean_push;        // lean formulation, without / with the peer stores of the halo push
   const char* name;
 };
 template <class C>
 constexpr FusedConfig make_fused(const char* name) {
   return FusedConfig{C::T, C::CJ, C::BJ, C::BK, C::BKP, C::HR, C::THREADS, C::SMEM_BYTES,
-                      upwind3d_fused_kernel<C>, name};
+                      upwind3d_fused_kernel<C>, upwind3d_fused_lean_kernel<C, false>, upwind3d_fused_lean_kernel<C, true>, name};
 }
 // per T: index 0 is the default, the rest are tuning alternatives (env FDB_FUSED_CFG)
 const FusedConfig kFused2[] = {
@@ -386,6 +571,9 @@ const FusedConfig* fz_pick(int T) {
   return &tab[c];
 }
 
+// measured on B200 (profiles/r02f_*): lean 914 vs 835 GCUPS at 512^3 (T=3), 847 vs 768 (T=4), 725 vs 747 (T=2)
+constexpr int fz_default_impl(int T) { return T >= 3 ? 2 : 1; }
+
 struct FusedAttr {
   const FusedConfig* cfg = nullptr;
   int ctas_per_sm = 1;
@@ -432,7 +620,8 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   const FusedConfig* C = fz_pick(T);
   if (!C) return set_error(FDB_E_INVALID, "no fused kernel for %d steps per sweep", T);
   if (at.cfg != C) {
-    FDB_CUDA(cudaFuncSetAttribute(C->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
+    for (FusedKernel kf : {C->kernel, C->lean, C->lean_push})
+      FDB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
     int nb = 0;
     FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C->kernel, C->threads, C->smem));
     if (nb < 1) return set_error(FDB_E_CUDA, "fused kernel %s does not fit on an SM", C->name);
@@ -485,7 +674,10 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
   // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
   if (const int cap = fz_env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;
-  C->kernel<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const FusedMaps*>(sl.fused_maps[X]), a);
+  // FDB_FUSED_IMPL: 1 = first consumer formulation, 2 = lean formulation
+  const int impl = fz_env_int("FDB_FUSED_IMPL", fz_default_impl(T));
+  const FusedKernel kf = (impl == 1) ? C->kernel : (peer_out ? C->lean_push : C->lean);
+  kf<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const FusedMaps*>(sl.fused_maps[X]), a);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;
