@@ -92,6 +92,7 @@ struct FusedArgs {
   double c0, c1, c2;
   double* peer_out;   // planes p >= peer_from are also stored here (the next slab's ghost planes), or null
   int64_t peer_from;
+  int64_t plane;      // n1 * n2
 };
 
 // Tensor maps: m[0..3] over the local planes, m[4..7] over the ghost planes below; box shapes
@@ -342,10 +343,16 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 //   * plane counters are 32-bit, the stage/barrier addresses advance by constants, output rows are R pointers that
 //     advance by one plane, idle threads of the last warp duplicate thread 0 instead of being predicated off, and
 //     the peer stores of the halo push live in their own instantiation (PUSH).
-template <class C, bool PUSH>
+//   * SPLIT: the exchange tile keeps the even cells (x) and the odd cells (y) of a row in two contiguous halves and
+//     only what a neighbour reads is stored (every row's y for the right-hand neighbour's k-1 operand, the last
+//     row's x for the j-1 operand of the thread below): the 8-byte accesses are conflict-free (2 shared-memory
+//     wavefronts per warp instead of the 4 of a 16-byte lane stride) -- 18 instead of 28 wavefronts per exchange.
+template <class C, bool PUSH, bool SPLIT>
 struct Lean {
   static constexpr int T = C::T, R = C::R;
   static constexpr uint32_t P = C::PITCH;
+  static constexpr uint32_t YOFF = C::PITCH / 2;   // y half of an exchange-tile row (TX <= PITCH / 16)
+  static_assert(!SPLIT || (C::TX + 1) * 8 <= C::PITCH / 2, "exchange row halves too narrow");
 
   struct State {
     uint32_t st;      // this thread's base inside the current stage
@@ -357,16 +364,19 @@ struct Lean {
     double* orow[C::R];   // output rows of the plane being computed
     double* prow[C::R];   // the same rows in the next slab's ghost planes (PUSH)
     int64_t plane_elems;
-    uint32_t smask;       // rows x columns this thread stores
+    uint32_t smask;       // rows x columns this thread stores; bit 31: the item is a first k-tile
     int lane;
   };
+  static constexpr uint32_t kFirstK = 0x80000000u;
 
   // one plane: level 0 comes from the stage, level s+1 from level s of this plane (X) and of the previous one (Pv)
   template <int PARITY>
   static __device__ __forceinline__ void step(State& z, double2 (&Pv)[C::T][C::R], double2 (&X)[C::T][C::R], bool store,
                                               bool push) {
-    mbar_wait(z.bar, z.par);
-    mbar_wait(z.bar - 8 * C::STAGES, z.par);  // already complete: orders this thread behind the TMA writes
+    // the TMA bytes of the stage have landed; only the first k-tile also waits for the loader warp's hand-over
+    // (its wrap columns are patched in after landing -- other tiles are complete as they land)
+    mbar_wait(z.bar - 8 * C::STAGES, z.par);
+    if (z.smask & kFirstK) mbar_wait(z.bar, z.par);
     double km[R];
     double2 up = lds_v2(z.st);
 #pragma unroll
@@ -404,18 +414,30 @@ struct Lean {
       } else {
         // hand level s+1 of this plane to the neighbours; the tiles alternate with every exchange
         const uint32_t xb = (((PARITY * (T - 1) + s) & 1) == 0) ? z.xt0 : z.xt1;
+        if (SPLIT) {
+          // z.xt0/z.xt1: row above the thread's first row, x half, this thread's slot (8 bytes per thread)
 #pragma unroll
-        for (int r = 0; r < R; ++r) sts_v2(xb + (1 + r) * P, X[s + 1][r].x, X[s + 1][r].y);
-        named_bar_sync(1, C::CONSUMERS);
-        up = lds_v2(xb);
+          for (int r = 0; r < R; ++r) sts_f64(xb + (1 + r) * P + YOFF, X[s + 1][r].y);
+          sts_f64(xb + R * P, X[s + 1][R - 1].x);
+          named_bar_sync(1, C::CONSUMERS);
+          up.x = lds_f64(xb);
+          up.y = lds_f64(xb + YOFF);
 #pragma unroll
-        for (int r = 0; r < R; ++r) km[r] = lds_f64(xb + (1 + r) * P - 8);
+          for (int r = 0; r < R; ++r) km[r] = lds_f64(xb + (1 + r) * P + YOFF - 8);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) sts_v2(xb + (1 + r) * P, X[s + 1][r].x, X[s + 1][r].y);
+          named_bar_sync(1, C::CONSUMERS);
+          up = lds_v2(xb);
+#pragma unroll
+          for (int r = 0; r < R; ++r) km[r] = lds_f64(xb + (1 + r) * P - 8);
+        }
       }
     }
   }
 };
 
-template <class C, bool PUSH>
+template <class C, bool PUSH, bool SPLIT>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
     upwind3d_fused_lean_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -443,7 +465,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     return;
   }
 
-  using L = Lean<C, PUSH>;
+  using L = Lean<C, PUSH, SPLIT>;
   // threads past the tile repeat thread 0's work (same values to the same shared-memory cells) and store nothing
   const bool worker = tid < C::WORKERS;
   const int wid = worker ? tid : 0;
@@ -458,8 +480,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   z.st = z.st0;
   z.bar = z.bar0;
   z.par = 0;
-  z.xt0 = xbuf + xt;
-  z.xt1 = xbuf + C::X_BYTES + xt;
+  // exchange tiles: interleaved rows (same offsets as the stage) or split halves (8 bytes per thread from the row start)
+  const uint32_t xx = SPLIT ? (uint32_t)(q0 * C::PITCH + 8 + tx * 8) : xt;
+  z.xt0 = xbuf + xx;
+  z.xt1 = xbuf + C::X_BYTES + xx;
   z.c0 = a.c0; z.c1 = a.c1; z.c2 = a.c2;
   z.plane_elems = a.n1 * a.n2;
   z.lane = lane;
@@ -477,6 +501,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;
     const int64_t j = (int64_t)jt * C::BJ - (C::T - 1) + q0;
     z.smask = (2 * tx >= C::HKC && k < a.n2) ? rowmask : 0u;
+    if (kt == 0) z.smask |= L::kFirstK;
 #pragma unroll
     for (int r = 0; r < C::R; ++r) {
       if (j + r >= a.n1) z.smask &= ~(1u << r);
@@ -513,38 +538,32 @@ struct FusedConfig {
   int T, CJ, BJ, BK, BKP, HR, threads, smem;
   FusedKernel kernel;                 // first consumer formulation (FDB_FUSED_IMPL=1)
   FusedKernel lean, lean_push;        // lean formulation, without / with the peer stores of the halo push
+  FusedKernel split, split_push;      // lean formulation with the split exchange-tile layout
   const char* name;
 };
 template <class C>
 constexpr FusedConfig make_fused(const char* name) {
   return FusedConfig{C::T, C::CJ, C::BJ, C::BK, C::BKP, C::HR, C::THREADS, C::SMEM_BYTES,
-                      upwind3d_fused_kernel<C>, upwind3d_fused_lean_kernel<C, false>, upwind3d_fused_lean_kernel<C, true>, name};
+                      upwind3d_fused_kernel<C>, upwind3d_fused_lean_kernel<C, false, false>, upwind3d_fused_lean_kernel<C, true, false>,
+                      upwind3d_fused_lean_kernel<C, false, true>, upwind3d_fused_lean_kernel<C, true, true>, name};
 }
 // per T: index 0 is the default, the rest are tuning alternatives (env FDB_FUSED_CFG)
+// per T: index 0 is the default, the rest are tuning alternatives (env FDB_FUSED_CFG).  Round-1/2 sweeps of tiles that
+// were dropped from the build since: six / seven rows per thread (7 warps), five rows, four rows (13 / 11 warps), 64-cell
+// tiles at two CTAs per SM, deeper stage rings -- all slower (profiles/r01c_*, r01l_*, r02i_sweep.txt).
 const FusedConfig kFused2[] = {
-    make_fused<FusedCfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),  // 760 GCUPS at 512^3 (profiles/r01n_*)
-    make_fused<FusedCfg<2, 18, 6, 4>>("t2_cj18_r6_s4"),  // 630
-    make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),  // 673
-    make_fused<FusedCfg<2, 18, 6, 6>>("t2_cj18_r6_s6"),  // 629
+    make_fused<FusedCfg<2, 21, 3, 5>>("t2_cj21_r3_s5"),
+    make_fused<FusedCfg<2, 16, 2, 4>>("t2_cj16_r2_s4"),
 };
 const FusedConfig kFused3[] = {
-    make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // 835 / 867 GCUPS at 512^3 / 1024^3 (profiles/r01l_*)
-    make_fused<FusedCfg<3, 18, 6, 4>>("t3_cj18_r6_s4"),  // six rows per thread: slower here (735 / 780)
-    make_fused<FusedCfg<3, 18, 6, 6>>("t3_cj18_r6_s6"),
-    make_fused<FusedCfg<3, 21, 7, 6>>("t3_cj21_r7_s6"),
-    make_fused<FusedCfg<3, 18, 3, 4, 64, 2>>("t3_cj18_r3_s4_bk64_2cta"),
-    make_fused<FusedCfg<3, 21, 3, 6>>("t3_cj21_r3_s6"),
-    make_fused<FusedCfg<3, 20, 5, 6>>("t3_cj20_r5_s6"),
-    make_fused<FusedCfg<3, 18, 3, 5>>("t3_cj18_r3_s5"),
-    // not yet timed on a B200: two rows per thread, 19 consumer warps at 96 registers (more warps in flight)
-    make_fused<FusedCfg<3, 18, 2, 4>>("t3_cj18_r2_s4"),
-    make_fused<FusedCfg<3, 18, 2, 3>>("t3_cj18_r2_s3"),
+    make_fused<FusedCfg<3, 21, 3, 4>>("t3_cj21_r3_s4"),  // 15 consumer warps x 3 rows
+    make_fused<FusedCfg<3, 18, 2, 4>>("t3_cj18_r2_s4"),  // 19 consumer warps x 2 rows
+    make_fused<FusedCfg<3, 24, 3, 4>>("t3_cj24_r3_s4"),  // 17 consumer warps x 3 rows, 10.8 % redundant halo
+    make_fused<FusedCfg<3, 18, 3, 4>>("t3_cj18_r3_s4"),  // 13 consumer warps x 3 rows
 };
 const FusedConfig kFused4[] = {
     make_fused<FusedCfg<4, 21, 3, 4>>("t4_cj21_r3_s4"),
-    make_fused<FusedCfg<4, 18, 3, 4>>("t4_cj18_r3_s4"),
-    make_fused<FusedCfg<4, 18, 6, 6>>("t4_cj18_r6_s6"),
-    make_fused<FusedCfg<4, 20, 4, 6>>("t4_cj20_r4_s6"),
+    make_fused<FusedCfg<4, 18, 2, 4>>("t4_cj18_r2_s4"),
 };
 
 const FusedConfig* fz_table(int T, int* count) {
@@ -571,8 +590,9 @@ const FusedConfig* fz_pick(int T) {
   return &tab[c];
 }
 
-// measured on B200 (profiles/r02f_*): lean 914 vs 835 GCUPS at 512^3 (T=3), 847 vs 768 (T=4), 725 vs 747 (T=2)
-constexpr int fz_default_impl(int T) { return T >= 3 ? 2 : 1; }
+// measured on B200 at 512^3 (profiles/r02f_*, r02h_*, r02j_*), first / lean / lean + split exchange tile:
+// T=3 835 / 915 / 973 GCUPS, T=4 768 / 850 / 939, T=2 747 / 720 / 715
+constexpr int fz_default_impl(int T) { return T >= 3 ? 4 : 1; }
 
 struct FusedAttr {
   const FusedConfig* cfg = nullptr;
@@ -620,7 +640,7 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   const FusedConfig* C = fz_pick(T);
   if (!C) return set_error(FDB_E_INVALID, "no fused kernel for %d steps per sweep", T);
   if (at.cfg != C) {
-    for (FusedKernel kf : {C->kernel, C->lean, C->lean_push})
+    for (FusedKernel kf : {C->kernel, C->lean, C->lean_push, C->split, C->split_push})
       FDB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
     int nb = 0;
     FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C->kernel, C->threads, C->smem));
@@ -651,6 +671,7 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   a.c2 = k.c[2];
   a.peer_out = peer_out;
   a.peer_from = peer_from;
+  a.plane = a.n1 * a.n2;
   const int reserve = f.single() ? 0 : fz_env_int("FDB_COMM_SMS", 0);  // SMs left free for NCCL halo kernels
   int64_t grid_max = (int64_t)at.ctas_per_sm * (at.sms - reserve);
   if (grid_max < 1) grid_max = 1;
@@ -674,9 +695,11 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
   // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
   if (const int cap = fz_env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;
-  // FDB_FUSED_IMPL: 1 = first consumer formulation, 2 = lean formulation
+  // FDB_FUSED_IMPL: 1 = first consumer formulation, 2 = lean, 4 = lean + split exchange tile
   const int impl = fz_env_int("FDB_FUSED_IMPL", fz_default_impl(T));
-  const FusedKernel kf = (impl == 1) ? C->kernel : (peer_out ? C->lean_push : C->lean);
+  const FusedKernel kf = (impl == 1)   ? C->kernel
+                         : (impl == 4) ? (peer_out ? C->split_push : C->split)
+                                       : (peer_out ? C->lean_push : C->lean);
   kf<<<(unsigned)grid, C->threads, C->smem, s>>>(*reinterpret_cast<const FusedMaps*>(sl.fused_maps[X]), a);
   count_launch();
   FDB_CUDA(cudaGetLastError());

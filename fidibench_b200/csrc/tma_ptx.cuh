@@ -76,6 +76,9 @@ __device__ __forceinline__ void fence_proxy_async_shared() {
 __device__ __forceinline__ void sts_v2(uint32_t addr, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
+__device__ __forceinline__ void sts_f64(uint32_t addr, double x) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
 // barrier among `nthreads` threads of the CTA (a multiple of 32), id 1..15
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
