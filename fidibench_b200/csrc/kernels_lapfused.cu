@@ -132,36 +132,15 @@ struct LapFusedCursor {
   }
 };
 
-template <class C, bool UNIT>
-__global__ void __launch_bounds__(C::THREADS, C::MINB)
-    lap7_fused2_kernel(const __grid_constant__ LapFusedMaps maps, const LapFusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
-  const uint32_t landed = xbuf + 2 * C::X_BYTES;      // TMA bytes of the stage have arrived
-  const uint32_t full = landed + C::STAGES * 8;       // ... and its wrap columns are in place
-  const uint32_t empty = full + C::STAGES * 8;        // every consumer warp has read the stage
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(landed + 8 * s, 1);
-      mbar_init(full + 8 * s, 1);
-      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == C::CONSUMER_WARPS) {
-    // ===================== loader warp =====================
-    // Lane 0 issues the TMA boxes of plane n; LAG planes behind, the warp waits for a plane to
-    // land, copies the periodic wrap columns of the first / last k-tile into the tile rows (one
-    // lane per row) and hands the stage to the consumers.  Issue waits for the consumers to free
-    // the stage of plane n - STAGES while planes up to n - STAGES + 1 are already handed over, so
-    // the two never wait for each other.
+// ===================== loader warp (shared by both consumer formulations) =====================
+// Lane 0 issues the TMA boxes of plane n; LAG planes behind, the warp waits for a plane to
+// land, copies the periodic wrap columns of the first / last k-tile into the tile rows (one
+// lane per row) and hands the stage to the consumers.  Issue waits for the consumers to free
+// the stage of plane n - STAGES while planes up to n - STAGES + 1 are already handed over, so
+// the two never wait for each other.
+template <class C>
+__device__ __forceinline__ void lapf_loader_warp(const LapFusedMaps& maps, const LapFusedArgs& a, uint32_t smem,
+                                                 uint32_t landed, uint32_t full, uint32_t empty, int lane) {
     if (lane == 0) {
 #pragma unroll
       for (int m = 0; m < 12; ++m) prefetch_tmap(&maps.m[m]);
@@ -229,6 +208,33 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
         --ahead;
       }
     }
+}
+
+template <class C, bool UNIT>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+    lap7_fused2_kernel(const __grid_constant__ LapFusedMaps maps, const LapFusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
+  const uint32_t landed = xbuf + 2 * C::X_BYTES;      // TMA bytes of the stage have arrived
+  const uint32_t full = landed + C::STAGES * 8;       // ... and its wrap columns are in place
+  const uint32_t empty = full + C::STAGES * 8;        // every consumer warp has read the stage
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    lapf_loader_warp<C>(maps, a, smem, landed, full, empty, lane);
     return;
   }
 
@@ -380,17 +386,221 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   }
 }
 
+// ---- lean consumer formulation (round 2) ------------------------------------------------------------------------
+// Same tile pipeline and the same arithmetic as lap7_fused2_kernel above, restated after the fused upwind kernel's
+// findings on B200 (profiles/r02e_*, r02j_*): FP64 instructions hold the issue port for two cycles and nothing
+// co-issues, and the shared-memory pipe is the second limiter.  So
+//   * the plane loop is unrolled by two and the register sets swap roles (level 0 of plane p / p-1, level 1 of
+//     plane p-1 / p-2): none of the 48 register moves per plane;
+//   * the exchange tile keeps the even cells (x) and the odd cells (y) of a row in two contiguous halves, so the
+//     k-1 / k+1 operands are conflict-free 8-byte loads (2 wavefronts instead of the 4 of a 16-byte lane stride);
+//   * 32-bit plane counters, output rows as pointers that advance by a plane, idle threads duplicate thread 0.
+template <class C, bool UNIT>
+struct LapLean {
+  static constexpr int R = C::R;
+  static constexpr uint32_t P = C::PITCH;
+  static constexpr uint32_t YOFF = C::PITCH / 2;  // y half of an exchange-tile row
+  static_assert((C::TX + 2) * 8 <= C::PITCH / 2, "exchange row halves too narrow");
+
+  struct State {
+    uint32_t st, bar, par, st0, bar0, bar_end;
+    uint32_t xt0, xt1;     // exchange tiles: row above the thread's first row, x half, this thread's slot
+    double* orow[C::R];    // output rows of plane p-2
+    int64_t plane_elems;
+    uint32_t smask;
+    int lane;
+  };
+
+  // one plane: level-0 plane p is in the stage; Cp = level 0 of plane p-1, Cc <- level 0 of plane p;
+  // Lp = level 1 of plane p-2, Lc <- level 1 of plane p-1; part1 / part2 = the six-branch partial sums
+  template <int PARITY>
+  static __device__ __forceinline__ void step(State& z, const LapFusedArgs& a, double2 (&Cp)[C::R], double2 (&Cc)[C::R],
+                                              double2 (&Lp)[C::R], double2 (&Lc)[C::R], double2 (&part1)[C::R],
+                                              double2 (&part2)[C::R], bool store) {
+    const double w0 = a.w[0], w1 = a.w[1], w2 = a.w[2], w3 = a.w[3], w4 = a.w[4], w5 = a.w[5], w6 = a.w[6];
+    mbar_wait(z.bar - 8 * C::STAGES, z.par);  // the TMA bytes have landed
+    mbar_wait(z.bar, z.par);                  // ... and the loader warp has patched the wrap columns
+    double km[R], kp[R];
+    const double2 up = lds_v2(z.st);
+    const double2 dn = lds_v2(z.st + (R + 1) * P);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      Cc[r] = lds_v2(z.st + (1 + r) * P);
+      km[r] = lds_f64(z.st + (1 + r) * P - 8);
+      kp[r] = lds_f64(z.st + (1 + r) * P + 16);
+    }
+    __syncwarp();
+    if (z.lane == 0) mbar_arrive(z.bar + 8 * C::STAGES);
+    z.st += C::STAGE_BYTES;
+    z.bar += 8;
+    if (z.bar == z.bar_end) { z.st = z.st0; z.bar = z.bar0; z.par ^= 1; }
+
+    // level 1 of plane p-1: the (+1,0,0) branch is this plane's centre
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      Lc[r].x = lf_acc<UNIT>(part1[r].x, w6, Cc[r].x);
+      Lc[r].y = lf_acc<UNIT>(part1[r].y, w6, Cc[r].y);
+    }
+    // level 2 of plane p-2: the (+1,0,0) branch is level 1 of plane p-1 -- done, store it
+    const uint32_t m = store ? z.smask : 0u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((m >> r) & 1u)
+        st_global_v2(z.orow[r], lf_acc<UNIT>(part2[r].x, w6, Lc[r].x), lf_acc<UNIT>(part2[r].y, w6, Lc[r].y));
+      z.orow[r] += z.plane_elems;
+    }
+    // hand level 1 of plane p-1 to the neighbours (both halves: the left neighbour reads x, the right one y)
+    const uint32_t xb = (PARITY == 0) ? z.xt0 : z.xt1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      sts_f64(xb + (1 + r) * P, Lc[r].x);
+      sts_f64(xb + (1 + r) * P + YOFF, Lc[r].y);
+    }
+    // first six branches of level 1 of plane p (keeps the FP64 pipe busy while warps gather)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double2 jm = (r == 0) ? up : Cc[r - 1];
+      const double2 jp = (r == R - 1) ? dn : Cc[r + 1];
+      double x = 0.0, y = 0.0;
+      x = lf_acc<UNIT>(x, w0, Cp[r].x);    y = lf_acc<UNIT>(y, w0, Cp[r].y);
+      x = lf_acc<UNIT>(x, w1, jm.x);       y = lf_acc<UNIT>(y, w1, jm.y);
+      x = lf_acc<UNIT>(x, w2, km[r]);      y = lf_acc<UNIT>(y, w2, Cc[r].x);
+      x = lf_acc<false>(x, w3, Cc[r].x);   y = lf_acc<false>(y, w3, Cc[r].y);
+      x = lf_acc<UNIT>(x, w4, Cc[r].y);    y = lf_acc<UNIT>(y, w4, kp[r]);
+      x = lf_acc<UNIT>(x, w5, jp.x);       y = lf_acc<UNIT>(y, w5, jp.y);
+      part1[r] = make_double2(x, y);
+    }
+    named_bar_sync(1, C::CONSUMERS);
+    // first six branches of level 2 of plane p-1 (rows outside the tile read the spare rows of the exchange tile:
+    // whatever is there only reaches level-2 rows that are never stored)
+    double2 up1, dn1;
+    up1.x = lds_f64(xb);
+    up1.y = lds_f64(xb + YOFF);
+    dn1.x = lds_f64(xb + (R + 1) * P);
+    dn1.y = lds_f64(xb + (R + 1) * P + YOFF);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      km[r] = lds_f64(xb + (1 + r) * P + YOFF - 8);  // y of the thread to the left
+      kp[r] = lds_f64(xb + (1 + r) * P + 8);         // x of the thread to the right
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double2 jm = (r == 0) ? up1 : Lc[r - 1];
+      const double2 jp = (r == R - 1) ? dn1 : Lc[r + 1];
+      double x = 0.0, y = 0.0;
+      x = lf_acc<UNIT>(x, w0, Lp[r].x);    y = lf_acc<UNIT>(y, w0, Lp[r].y);
+      x = lf_acc<UNIT>(x, w1, jm.x);       y = lf_acc<UNIT>(y, w1, jm.y);
+      x = lf_acc<UNIT>(x, w2, km[r]);      y = lf_acc<UNIT>(y, w2, Lc[r].x);
+      x = lf_acc<false>(x, w3, Lc[r].x);   y = lf_acc<false>(y, w3, Lc[r].y);
+      x = lf_acc<UNIT>(x, w4, Lc[r].y);    y = lf_acc<UNIT>(y, w4, kp[r]);
+      x = lf_acc<UNIT>(x, w5, jp.x);       y = lf_acc<UNIT>(y, w5, jp.y);
+      part2[r] = make_double2(x, y);
+    }
+  }
+};
+
+template <class C, bool UNIT>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+    lap7_fused2_lean_kernel(const __grid_constant__ LapFusedMaps maps, const LapFusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t xbuf = smem + C::STAGES * C::STAGE_BYTES;
+  const uint32_t landed = xbuf + 2 * C::X_BYTES;
+  const uint32_t full = landed + C::STAGES * 8;
+  const uint32_t empty = full + C::STAGES * 8;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(landed + 8 * s, 1);
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, C::CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == C::CONSUMER_WARPS) {
+    lapf_loader_warp<C>(maps, a, smem, landed, full, empty, lane);
+    return;
+  }
+
+  using L = LapLean<C, UNIT>;
+  const bool worker = tid < C::WORKERS;
+  const int wid = worker ? tid : 0;  // threads past the tile repeat thread 0's work and store nothing
+  const int tx = wid % C::TX;
+  const int ty = wid / C::TX;
+  const int q0 = ty * C::R;
+  typename L::State z;
+  z.st0 = smem + q0 * C::PITCH + 16 + tx * 16;
+  z.bar0 = full;
+  z.bar_end = full + 8 * C::STAGES;
+  z.st = z.st0;
+  z.bar = z.bar0;
+  z.par = 0;
+  z.xt0 = xbuf + q0 * C::PITCH + 8 + tx * 8;
+  z.xt1 = z.xt0 + C::X_BYTES;
+  z.plane_elems = a.n1 * a.n2;
+  z.lane = lane;
+  uint32_t rowmask = 0;
+#pragma unroll
+  for (int r = 0; r < C::R; ++r)
+    if (worker && tx >= 1 && tx <= C::TX - 2 && q0 + r >= 1 && q0 + r <= C::CJ - 2) rowmask |= 1u << r;
+  z.smask = rowmask;
+
+  double2 C0[C::R], C1[C::R], L0[C::R], L1[C::R], part1[C::R], part2[C::R];
+#pragma unroll
+  for (int r = 0; r < C::R; ++r)
+    C0[r] = C1[r] = L0[r] = L1[r] = part1[r] = part2[r] = make_double2(0.0, 0.0);
+
+  for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
+    const int kt = (int)(w % a.nkt);
+    const int jt = (int)((w / a.nkt) % a.njt);
+    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t i0 = a.ibeg + ic * a.ci;
+    const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
+    const int64_t k = (int64_t)kt * C::BK - 2 + 2 * tx;
+    const int64_t j = (int64_t)jt * C::BJ - 1 + q0;
+    // rows of plane i0 - 4: the step that loads plane p stores plane p - 2, and the first step loads plane i0 - 2
+#pragma unroll
+    for (int r = 0; r < C::R; ++r) z.orow[r] = a.out + ((i0 - 4) * a.n1 + j + r) * a.n2 + k;
+    // planes i0-2 .. i1+1; the step q (from 0) stores plane i0 - 4 + q, valid from q = 4 on.  The register sets are
+    // not reset between items: a level is only read once every plane it depends on has been loaded by this item.
+    const int np = (int)(i1 - i0) + 4;
+    int q = 0;
+    for (; q + 2 <= np; q += 2) {
+      L::template step<0>(z, a, C0, C1, L0, L1, part1, part2, q >= 4);
+      L::template step<1>(z, a, C1, C0, L1, L0, part1, part2, q + 1 >= 4);
+    }
+    if (q < np) {
+      L::template step<0>(z, a, C0, C1, L0, L1, part1, part2, q >= 4);
+      // odd plane count: the sets swap by value (once per item), and the next item's first plane must not write
+      // the exchange tile this plane's neighbours may still be reading
+#pragma unroll
+      for (int r = 0; r < C::R; ++r) {
+        double2 t = C0[r]; C0[r] = C1[r]; C1[r] = t;
+        t = L0[r]; L0[r] = L1[r]; L1[r] = t;
+      }
+      named_bar_sync(1, C::CONSUMERS);
+    }
+  }
+}
+
 // ---- configurations ---------------------------------------------------------------------
 typedef void (*LapFusedKernel)(const LapFusedMaps, const LapFusedArgs);
 struct LapFusedConfig {
   int BJ, BK, BKP, threads, smem;
   LapFusedKernel kernel_unit, kernel_general;  // off-centre weights all exactly 1.0 / any weights
+  LapFusedKernel lean_unit, lean_general;      // lean consumer formulation (FDB_LAPF_IMPL=2)
   const char* name;
 };
 template <class C>
 constexpr LapFusedConfig make_lapf(const char* name) {
   return LapFusedConfig{C::BJ, C::BK, C::BKP, C::THREADS, C::SMEM_BYTES, lap7_fused2_kernel<C, true>,
-                        lap7_fused2_kernel<C, false>, name};
+                        lap7_fused2_kernel<C, false>, lap7_fused2_lean_kernel<C, true>, lap7_fused2_lean_kernel<C, false>,
+                        name};
 }
 // kDefaultLapFused is the default (round-1 sweeps on a B200, profiles/r01j_*: six rows per thread,
 // 7 consumer warps, 242 registers -- 639 GCUPS at 1024^3, 611 at 512^3); the rest are tuning
@@ -414,6 +624,10 @@ const LapFusedConfig kLapFused[] = {
 };
 constexpr int kNumLapFused = sizeof(kLapFused) / sizeof(kLapFused[0]);
 constexpr int kDefaultLapFused = 7;  // bj16_r6_s6
+// measured on B200 (profiles/r02k_*): both formulations run 652 GCUPS at 1024^3 in every tile configuration that used to
+// differ (580..653 before) -- the kernel sits at 82 % of the measured copy bandwidth in DRAM traffic; the lean one
+// issues 20 % fewer instructions for it
+constexpr int kDefaultLapFusedImpl = 2;
 
 int lf_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -487,7 +701,8 @@ int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend
   bool unit = lf_env_int("FDB_LAPF_GENERAL", 0) == 0;
   for (int i = 0; i < 7; ++i)
     if (lapf_slot(b.off[i]) != 3 && b.w[i] != 1.0) unit = false;
-  const LapFusedKernel fn = unit ? C->kernel_unit : C->kernel_general;
+  const int impl = lf_env_int("FDB_LAPF_IMPL", kDefaultLapFusedImpl);  // 1 = first consumer formulation, 2 = lean
+  const LapFusedKernel fn = (impl == 2) ? (unit ? C->lean_unit : C->lean_general) : (unit ? C->kernel_unit : C->kernel_general);
   LapFusedAttr& at = g_lapf_attr[sl.device & 15];
   if (at.fn != fn) {
     FDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C->smem));
