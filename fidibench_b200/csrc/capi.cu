@@ -47,8 +47,19 @@ struct UpwindSweep : SweepLauncher {
     return tma ? launch_upwind_tma(*f, d, X, ibeg, iend, k, s)
                : launch_upwind_generic(*f, d, X, ibeg, iend, k, s);
   }
+  int prepare(Field* f, int d, int depth) override {
+    FDB_TRY(generic_kernels_prepare());
+    if (depth > 1) return upwind_fused_prepare(*f, d, depth);
+    return tma ? upwind_tma_prepare(*f, d) : FDB_OK;
+  }
   // the TMA kernels can mirror their top planes into the next slab's ghost planes themselves
   bool can_push(const Field*, int) const override { return tma; }
+  bool can_push_single(const Field*, int depth) const override { return tma && depth > 1 && upwind_fused_can_signal(depth); }
+  int launch_single(Field* f, int d, int X, int depth, cudaStream_t s, double* peer_out, int64_t peer_from,
+                    const HaloSignal& sig) override {
+    if (!can_push_single(f, depth)) return FDB_E_STATE;
+    return launch_upwind_fused(*f, d, X, depth, 0, f->slabs[d].nloc(), k, s, peer_out, peer_from, &sig);
+  }
   uint64_t key() const override {
     uint64_t h = tma ? 0x51ull : 0x77ull;
     for (int a = 0; a < 3; ++a) {
@@ -71,6 +82,11 @@ struct StencilSweep : SweepLauncher {
   const StencilBranches* b = nullptr;
   bool fast = false;
   int fused_depth = 0;  // sweeps of this ghost depth run the two-applies-per-sweep kernel (0 = never)
+  int prepare(Field* f, int d, int depth) override {
+    FDB_TRY(generic_kernels_prepare());
+    if (fused_depth > 0 && depth == fused_depth) return stencil_lap7_fused_prepare(*f, d, *b);
+    return fast ? stencil_lap7_prepare(*f, d) : FDB_OK;
+  }
   uint64_t key() const override {  // the branches live in the handle and never change after creation
     return (0xF17ull * 0x100000001B3ull) ^ ((uint64_t)fast << 1) ^ ((uint64_t)fused_depth << 4) ^ ((uint64_t)b->ref_wrap << 9) | 1ull;
   }

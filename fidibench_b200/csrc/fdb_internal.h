@@ -183,6 +183,19 @@ int field_plane_sums(Field* f, int p, double* planes_out);  // geo.n[0] per-plan
 // travelling while the interior is computed), ghosts of the new field exchanged, buffers not
 // swapped.  `launch(f, d, X, ibeg, iend, stream)` must enqueue the kernel computing local planes
 // [ibeg,iend) of buf[1-X] from buf[X] on slab d; `depth` is set per sweep by the plan.
+// Device-side completion protocol of a single-launch ring sweep (kernels_fused.cu): the kernel waits for
+// *ack_flag >= ack_value before its first peer store and sets *nbr_flag = flag_value behind its last one.
+struct HaloSignal {
+  unsigned int* done_ctr = nullptr;
+  unsigned long long* nbr_flag = nullptr;
+  unsigned long long flag_value = 0;
+  const unsigned long long* ack_flag = nullptr;
+  unsigned long long ack_value = 0;
+  // the kernel's loader waits for *ghost_flag >= ghost_value before it reads this slab's ghost planes
+  const unsigned long long* ghost_flag = nullptr;
+  unsigned long long ghost_value = 0;
+};
+
 struct SweepLauncher {
   virtual int launch(Field* f, int d, int X, int depth, int64_t ibeg, int64_t iend, cudaStream_t s) = 0;
   // Fused halo push: same as launch(), and the kernel also stores local planes >= peer_from through
@@ -193,6 +206,18 @@ struct SweepLauncher {
     return FDB_E_STATE;
   }
   virtual bool can_push(const Field*, int /*depth*/) const { return false; }
+  // One-time set-up of whatever kernel a sweep of this depth launches on slab d (function attributes, occupancy,
+  // tensor maps, module load).  Such calls may synchronise the device or take driver-wide locks, so multi-device
+  // fields make them all up front: once a stream waits on another device's counter, a host thread that blocks in one
+  // of them while holding a driver lock can keep the thread that would raise that counter from enqueuing its work.
+  virtual int prepare(Field*, int /*d*/, int /*depth*/) { return FDB_OK; }
+  // Single-launch ring sweep: ONE kernel over the whole slab that walks the top chunk first, stores the planes the next
+  // slab reads through `peer_out` and runs the HaloSignal protocol itself.  FDB_E_STATE when the launcher cannot.
+  virtual bool can_push_single(const Field*, int /*depth*/) const { return false; }
+  virtual int launch_single(Field*, int /*d*/, int /*X*/, int /*depth*/, cudaStream_t, double* /*peer_out*/,
+                            int64_t /*peer_from*/, const HaloSignal&) {
+    return FDB_E_STATE;
+  }
   // Everything the launches bake in besides (field, parity, depths): two launchers with the same non-zero key
   // enqueue identical kernels, so a captured CUDA graph of a sweep plan can be replayed.  0 = do not cache.
   virtual uint64_t key() const { return 0; }
@@ -214,7 +239,12 @@ int launch_upwind_generic(const Field& f, int d, int X, int64_t ibeg, int64_t ie
 bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k);
 bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T);
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                        cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0);
+                        cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0, const HaloSignal* sig = nullptr);
+bool upwind_fused_can_signal(int T);
+int upwind_fused_prepare(Field& f, int d, int T);
+int upwind_tma_prepare(const Field& f, int d);
+int stencil_lap7_prepare(const Field& f, int d);
+int generic_kernels_prepare();  // the selected consumer formulation runs the HaloSignal protocol
 const char* upwind_fused_name(int T);
 // peer_out/peer_from: planes >= peer_from are also stored into the next slab's ghost planes
 int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
@@ -236,6 +266,7 @@ bool stencil_lap7_fused_supported(const Field& f, const StencilBranches& b);
 int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
                               cudaStream_t s);
 const char* stencil_lap7_fused_name(const Field& f);
+int stencil_lap7_fused_prepare(Field& f, int d, const StencilBranches& b);
 
 int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode, double mean,
                       double* partial, double* plane_sums, cudaStream_t s);

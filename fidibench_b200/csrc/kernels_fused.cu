@@ -34,6 +34,8 @@
 // Arithmetic per level is exactly the single step's (separately rounded, reference order,
 // ref: upwind/cxx/upwind.cxx:72-80), so T fused steps are bit-identical to T single steps.
 // tests/host_model_fused.py restates the tile pipeline with numpy and is pinned to the oracle.
+#include <algorithm>
+
 #include "fdb_internal.h"
 #include "tma_ptx.cuh"
 
@@ -93,7 +95,34 @@ struct FusedArgs {
   double* peer_out;   // planes p >= peer_from are also stored here (the next slab's ghost planes), or null
   int64_t peer_from;
   int64_t plane;      // n1 * n2
+  // single-launch sweeps on a slab ring (runtime.cu: sweep_device_direct): the chunks are walked top chunk first, the
+  // work items that hold pushed planes wait for the neighbour's ACK before their first peer store, and the last of
+  // them to finish raises the neighbour's ghost flag -- no separate boundary launch, no host or stream in between
+  int nchunks, reverse;           // chunks along the marching axis; reverse: chunk nchunks-1 first
+  unsigned int* done_ctr;         // items with pushed planes finished so far (device memory of this slab), or null
+  unsigned int done_target;
+  unsigned long long* nbr_flag;   // the next slab's F_GHOST_LO counter (peer-mapped) <- flag_value when all are done
+  unsigned long long flag_value;
+  const unsigned long long* ack_flag;  // this slab's F_ACK_NEXT counter: wait for >= ack_value before the first peer store
+  unsigned long long ack_value;
+  const unsigned long long* ghost_flag;  // this slab's F_GHOST_LO counter: the loader waits for >= ghost_value before
+  unsigned long long ghost_value;        // its first load from the ghost planes (null: the stream waited already)
+  int64_t peer_delta;  // byte distance from a stored cell of `out` to the same cell in the next slab's ghost planes
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// chunk of work item w along the marching axis (top chunk first on single-launch ring sweeps)
+__device__ __forceinline__ int64_t fz_chunk_of(const FusedArgs& a, int64_t w) {
+  const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+  return a.reverse ? (int64_t)a.nchunks - 1 - ic : ic;
+}
 
 // Tensor maps: m[0..3] over the local planes, m[4..7] over the ghost planes below; box shapes
 //   0/4: {BKP, HR} halo rows   1/5: {BKP, BJ} tile rows   2/6: {8, HR} wrap corner   3/7: {8, BJ} wrap columns
@@ -119,7 +148,7 @@ struct FusedCursor {
   __device__ __forceinline__ void open(const FusedArgs& a) {
     kt = (int)(w % a.nkt);
     jt = (int)((w / a.nkt) % a.njt);
-    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t ic = fz_chunk_of(a, w);
     const int64_t i0 = a.ibeg + ic * a.ci;
     i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
     p = i0 - C::T;
@@ -150,10 +179,18 @@ __device__ __forceinline__ void fused_loader_warp(const FusedMaps& maps, const F
     int si = 0, sf = 0;
     uint32_t phi = 0, phf = 0;
     int ahead = 0;
+    bool ghosts_seen = false;
     while (cf.valid(a)) {
       if (ci.valid(a)) {
         mbar_wait(empty + 8 * si, phi ^ 1);
         if (lane == 0) {
+          if (ci.p < 0 && a.ghost_flag != nullptr && !ghosts_seen) {
+            // single-launch ring sweep: the ghost planes are the previous slab's peer stores; its kernel raises this
+            // counter behind the last of them (the bottom chunk comes last here, so this rarely spins)
+            while (ld_acquire_sys_u64(a.ghost_flag) < a.ghost_value) {}
+            fence_proxy_async_all();  // ... and the TMA reads below go through the async proxy
+            ghosts_seen = true;
+          }
           const uint32_t st = smem + si * C::STAGE_BYTES;
           const uint32_t lb = landed + 8 * si;
           const int kb = ci.kt * C::BK - 8;  // first stage column (negative for the first k-tile: zero fill)
@@ -251,7 +288,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     const int kt = (int)(w % a.nkt);
     const int jt = (int)((w / a.nkt) % a.njt);
-    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t ic = fz_chunk_of(a, w);
     const int64_t i0 = a.ibeg + ic * a.ci;
     const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
     const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;   // global column of this thread's first cell
@@ -362,8 +399,8 @@ struct Lean {
     uint32_t xt0, xt1;  // this thread's base inside the two exchange tiles
     double c0, c1, c2;
     double* orow[C::R];   // output rows of the plane being computed
-    double* prow[C::R];   // the same rows in the next slab's ghost planes (PUSH)
     int64_t plane_elems;
+    int64_t peer_delta;   // PUSH: byte distance to the same cell in the next slab's ghost planes
     uint32_t smask;       // rows x columns this thread stores; bit 31: the item is a first k-tile
     int lane;
   };
@@ -402,14 +439,16 @@ struct Lean {
         if (s == T - 1) out[r] = n; else X[s + 1][r] = n;
       }
       if (s == T - 1) {
+        if (PUSH && push) {  // uniform over the CTA: the planes the next slab reads as ghosts
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((m >> r) & 1u)
+              st_global_v2(reinterpret_cast<double*>(reinterpret_cast<char*>(z.orow[r]) + z.peer_delta), out[r].x, out[r].y);
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if ((m >> r) & 1u) {
-            st_global_v2(z.orow[r], out[r].x, out[r].y);
-            if (PUSH && push) st_global_v2(z.prow[r], out[r].x, out[r].y);
-          }
+          if ((m >> r) & 1u) st_global_v2(z.orow[r], out[r].x, out[r].y);
           z.orow[r] += z.plane_elems;
-          if (PUSH) z.prow[r] += z.plane_elems;
         }
       } else {
         // hand level s+1 of this plane to the neighbours; the tiles alternate with every exchange
@@ -486,6 +525,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   z.xt1 = xbuf + C::X_BYTES + xx;
   z.c0 = a.c0; z.c1 = a.c1; z.c2 = a.c2;
   z.plane_elems = a.n1 * a.n2;
+  z.peer_delta = PUSH ? a.peer_delta : 0;
   z.lane = lane;
   uint32_t rowmask = 0;
 #pragma unroll
@@ -495,7 +535,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
   for (int64_t w = blockIdx.x; w < a.nwork; w += gridDim.x) {
     const int kt = (int)(w % a.nkt);
     const int jt = (int)((w / a.nkt) % a.njt);
-    const int64_t ic = w / ((int64_t)a.nkt * a.njt);
+    const int64_t ic = fz_chunk_of(a, w);
     const int64_t i0 = a.ibeg + ic * a.ci;
     const int64_t i1 = (i0 + a.ci < a.iend) ? i0 + a.ci : a.iend;
     const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;
@@ -507,7 +547,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
       if (j + r >= a.n1) z.smask &= ~(1u << r);
       // rows of plane i0 - T (the first warm-up plane: never dereferenced before plane i0)
       z.orow[r] = a.out + ((i0 - C::T) * a.n1 + j + r) * a.n2 + k;
-      if (PUSH) z.prow[r] = a.peer_out + ((i0 - C::T - a.peer_from) * a.n1 + j + r) * a.n2 + k;
     }
     double2 A[C::T][C::R], B[C::T][C::R];  // levels 0..T-1 of the previous plane / of this plane, swapping roles
 #pragma unroll
@@ -518,16 +557,47 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     // T warm-up planes below the chunk, then the chunk; `q` counts planes from i0 - T
     const int np = (int)(i1 - i0) + C::T;
     const int push_from = PUSH ? (int)(a.peer_from - (i0 - C::T)) : 0;
+    // single-launch ring sweep: this item holds planes the next slab reads as ghosts
+    const bool signals = PUSH && a.done_ctr != nullptr && i1 > a.peer_from;
+    const int ack_at = push_from > C::T ? push_from : C::T;  // first plane-step that stores to the peer
     int q = 0;
     for (; q + 2 <= np; q += 2) {
+      if (signals && (q == ack_at || q + 1 == ack_at)) {
+        // WAR on the neighbour's ghost planes: it has finished the sweep that read them (its ACK, written by a stream
+        // memory operation behind that sweep, lands in this slab's memory)
+        if (tid == 0)
+          while (ld_acquire_sys_u64(a.ack_flag) < a.ack_value) {}
+        __syncwarp();
+        named_bar_sync(1, C::CONSUMERS);
+      }
       L::template step<0>(z, A, B, q >= C::T, q >= push_from);
       L::template step<1>(z, B, A, q + 1 >= C::T, q + 1 >= push_from);
     }
     if (q < np) {
+      if (signals && q == ack_at) {
+        if (tid == 0)
+          while (ld_acquire_sys_u64(a.ack_flag) < a.ack_value) {}
+        __syncwarp();
+        named_bar_sync(1, C::CONSUMERS);
+      }
       // odd plane count: one more plane in the even roles (the next item starts from zeroed sets anyway)
       L::template step<0>(z, A, B, q >= C::T, q >= push_from);
       // with an odd number of exchanges per plane the next item would write the exchange tile this plane just read
       if ((C::T - 1) & 1) named_bar_sync(1, C::CONSUMERS);
+    }
+    if (signals) {
+      // every peer store of this item is issued; the last item to get here publishes them to the neighbour
+      named_bar_sync(1, C::CONSUMERS);
+      if (tid == 0) {
+        __threadfence_system();
+        const unsigned int done = atomicAdd(a.done_ctr, 1u) + 1u;
+        if (done == a.done_target) {
+          __threadfence_system();
+          *a.done_ctr = 0u;  // the next sweep's kernel is ordered behind this one
+          st_release_sys_u64(a.nbr_flag, a.flag_value);
+        }
+      }
+      __syncwarp();
     }
   }
 }
@@ -632,9 +702,7 @@ const char* upwind_fused_name(int T) {
   return C ? C->name : "";
 }
 
-int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                         cudaStream_t s, double* peer_out, int64_t peer_from) {
-  if (iend <= ibeg) return FDB_OK;
+int upwind_fused_prepare(Field& f, int d, int T) {
   Slab& sl = f.slabs[d];
   FusedAttr& at = g_fz_attr[sl.device & 15][T];
   const FusedConfig* C = fz_pick(T);
@@ -657,6 +725,18 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
     sl.fused_T = T;
     sl.fused_cfg = (const void*)C;
   }
+  return FDB_OK;
+}
+
+bool upwind_fused_can_signal(int T) { return fz_env_int("FDB_FUSED_IMPL", fz_default_impl(T)) != 1; }
+
+int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                         cudaStream_t s, double* peer_out, int64_t peer_from, const HaloSignal* sig) {
+  if (iend <= ibeg) return FDB_OK;
+  FDB_TRY(upwind_fused_prepare(f, d, T));
+  Slab& sl = f.slabs[d];
+  FusedAttr& at = g_fz_attr[sl.device & 15][T];
+  const FusedConfig* C = fz_pick(T);
   FusedArgs a;
   a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];
@@ -691,7 +771,36 @@ int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t ien
   }
   if (ci > planes) ci = planes;
   a.ci = (int)ci;
-  a.nwork = tiles * ((planes + ci - 1) / ci);
+  a.nchunks = (int)((planes + ci - 1) / ci);
+  a.nwork = tiles * a.nchunks;
+  a.reverse = 0;
+  a.done_ctr = nullptr;
+  a.done_target = 0;
+  a.nbr_flag = nullptr;
+  a.flag_value = 0;
+  a.ack_flag = nullptr;
+  a.ack_value = 0;
+  a.ghost_flag = nullptr;
+  a.ghost_value = 0;
+  a.peer_delta = peer_out ? (int64_t)((char*)peer_out - (char*)a.out) - peer_from * a.plane * (int64_t)sizeof(double) : 0;
+  if (sig) {
+    if (!peer_out || !upwind_fused_can_signal(T))
+      return set_error(FDB_E_STATE, "this fused kernel formulation cannot signal its halo push");
+    int64_t pushing = 0;  // chunks that hold planes >= peer_from
+    for (int64_t c = 0; c < a.nchunks; ++c) {
+      const int64_t c1 = std::min<int64_t>(ibeg + (c + 1) * ci, iend);
+      if (c1 > peer_from) ++pushing;
+    }
+    a.reverse = 1;
+    a.done_ctr = sig->done_ctr;
+    a.done_target = (unsigned int)(tiles * pushing);
+    a.nbr_flag = sig->nbr_flag;
+    a.flag_value = sig->flag_value;
+    a.ack_flag = sig->ack_flag;
+    a.ack_value = sig->ack_value;
+    a.ghost_flag = sig->ghost_flag;
+    a.ghost_value = sig->ghost_value;
+  }
   int64_t grid = a.nwork < grid_max ? a.nwork : grid_max;
   // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
   if (const int cap = fz_env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;

@@ -316,6 +316,18 @@ int launch_stencil_generic(const Field& f, int d, int X, int64_t ibeg, int64_t i
   return FDB_OK;
 }
 
+// forces the (lazily loaded) generic kernels onto the current device; see SweepLauncher::prepare
+int generic_kernels_prepare() {
+  cudaFuncAttributes fa;
+  FDB_CUDA(cudaFuncGetAttributes(&fa, upwind_generic_kernel));
+  FDB_CUDA(cudaFuncGetAttributes(&fa, stencil_generic_kernel));
+  FDB_CUDA(cudaFuncGetAttributes(&fa, fill_kernel));
+  FDB_CUDA(cudaFuncGetAttributes(&fa, mirror_kernel));
+  FDB_CUDA(cudaFuncGetAttributes(&fa, plane_partial_kernel));
+  FDB_CUDA(cudaFuncGetAttributes(&fa, plane_final_kernel));
+  return FDB_OK;
+}
+
 int64_t reduce_partials_per_plane(int64_t plane) { return (plane + kChunk - 1) / kChunk; }
 
 int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode, double mean,

@@ -690,9 +690,9 @@ static int lapf_maps(const Field& f, int d, const LapFusedConfig& C, int p, LapF
   return FDB_OK;
 }
 
-int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
-                              cudaStream_t s) {
-  if (iend <= ibeg) return FDB_OK;
+// one-time, per-device set-up (function attributes, occupancy, tensor maps); see SweepLauncher::prepare
+static int lapf_prepare(Field& f, int d, const StencilBranches& b, const LapFusedConfig** Cout, LapFusedKernel* fnout,
+                        LapFusedAttr** atout) {
   Slab& sl = f.slabs[d];
   const LapFusedConfig* C = lapf_pick(f);
   if (!C) return set_error(FDB_E_INVALID, "no fused 7-point tile divides a %lld x %lld plane",
@@ -719,6 +719,23 @@ int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend
     for (int p = 0; p < 2; ++p) FDB_TRY(lapf_maps(f, d, *C, p, reinterpret_cast<LapFusedMaps*>(sl.lapf_maps[p])));
     sl.lapf_cfg = (const void*)C;
   }
+  if (Cout) *Cout = C;
+  if (fnout) *fnout = fn;
+  if (atout) *atout = &at;
+  return FDB_OK;
+}
+
+int stencil_lap7_fused_prepare(Field& f, int d, const StencilBranches& b) { return lapf_prepare(f, d, b, nullptr, nullptr, nullptr); }
+
+int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
+                              cudaStream_t s) {
+  if (iend <= ibeg) return FDB_OK;
+  const LapFusedConfig* C = nullptr;
+  LapFusedKernel fn = nullptr;
+  LapFusedAttr* atp = nullptr;
+  FDB_TRY(lapf_prepare(f, d, b, &C, &fn, &atp));
+  LapFusedAttr& at = *atp;
+  Slab& sl = f.slabs[d];
   LapFusedArgs a;
   a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];

@@ -518,10 +518,12 @@ bool upwind_tma_supported(const Field& f, const UpwindCoeffs& k) {
   return true;
 }
 
-int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
-                      cudaStream_t s, double* peer_out, int64_t peer_from) {
-  if (iend <= ibeg) return FDB_OK;
+// One-time, per-device set-up of the kernel (function attributes, occupancy: calls that may load the module and
+// synchronise the device).  Also reachable through SweepLauncher::prepare, which multi-device fields call BEFORE
+// they enqueue anything that waits on another device's counters.
+int upwind_tma_prepare(const Field& f, int d) {
   const Slab& sl = f.slabs[d];
+  if (!sl.have_tma) return FDB_OK;
   const UpwindTmaConfig& C = kUpCfgs[sl.tma_cfg];
   KernelAttr& at = g_up_attr[sl.device & 15][sl.tma_cfg];
   if (!at.done) {
@@ -534,6 +536,16 @@ int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, 
     at.sms = prop.multiProcessorCount;
     at.done = true;
   }
+  return FDB_OK;
+}
+
+int launch_upwind_tma(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
+                      cudaStream_t s, double* peer_out, int64_t peer_from) {
+  if (iend <= ibeg) return FDB_OK;
+  const Slab& sl = f.slabs[d];
+  const UpwindTmaConfig& C = kUpCfgs[sl.tma_cfg];
+  KernelAttr& at = g_up_attr[sl.device & 15][sl.tma_cfg];
+  FDB_TRY(upwind_tma_prepare(f, d));
   UpwindTmaArgs a;
   a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];
@@ -665,10 +677,9 @@ bool stencil_lap7_supported(const Field& f, const StencilBranches& b) {
   return true;
 }
 
-int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
-                        cudaStream_t s) {
-  if (iend <= ibeg) return FDB_OK;
+int stencil_lap7_prepare(const Field& f, int d) {
   const Slab& sl = f.slabs[d];
+  if (!sl.have_tma) return FDB_OK;
   const Lap7Config& C = kLapCfgs[sl.tma_cfg];
   KernelAttr& at = g_lap_attr[sl.device & 15][sl.tma_cfg];
   if (!at.done) {
@@ -681,6 +692,16 @@ int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend
     at.sms = prop.multiProcessorCount;
     at.done = true;
   }
+  return FDB_OK;
+}
+
+int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
+                        cudaStream_t s) {
+  if (iend <= ibeg) return FDB_OK;
+  const Slab& sl = f.slabs[d];
+  const Lap7Config& C = kLapCfgs[sl.tma_cfg];
+  KernelAttr& at = g_lap_attr[sl.device & 15][sl.tma_cfg];
+  FDB_TRY(stencil_lap7_prepare(f, d));
   Lap7Args a;
   a.out = f.body(d, 1 - X);
   a.n1 = f.geo.n[1];

@@ -73,6 +73,11 @@ __device__ __forceinline__ void fence_proxy_async_shared() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ... for every state space (global data another GPU wrote, about to be read by TMA)
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 __device__ __forceinline__ void sts_v2(uint32_t addr, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }

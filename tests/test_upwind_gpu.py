@@ -344,3 +344,30 @@ def test_default_dt_is_positive_for_negative_velocities(gpu_fb):
         out = up.field()
     assert np.array_equal(out, C.upwind_advect(a, 6, velocity=vel, dt=dt))
     assert abs(out).max() <= abs(a).max()   # a stable (monotone) step, not an anti-diffusive one
+
+
+@pytest.mark.parametrize("halo", ["single", "copy"])
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_slab_ring_halo_transports_agree(gpu_fb, ngpus, halo, monkeypatch):
+    """The default on a one-sided ring is a boundary launch that pushes its planes with peer stores + an interior
+    launch; FDB_HALO=single runs ONE launch per sweep (top chunk first, device-side ACK / ghost waits and ghost flag),
+    FDB_HALO=copy the copy engines.  All three must give the single-domain oracle's bits, over plans that mix sweep
+    depths and repeated calls."""
+    if gpu_fb.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(SEED + 60)
+    a = rng.random((40 * ngpus, 45, 260))
+
+    def run():
+        with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape, ngpus=ngpus) as up:
+            up.set_field(a)
+            dt = up.default_dt()
+            for n in (10, 3, 7, 1, 12):
+                up.advect(n, dt)
+            return up.field(), dt
+
+    ref_default, dt = run()
+    assert np.array_equal(ref_default, C.upwind_advect(a, 33, dt=dt))
+    monkeypatch.setenv("FDB_HALO", halo)
+    other, _ = run()
+    assert np.array_equal(other, ref_default)
