@@ -92,6 +92,11 @@ class Upwind {
     for (size_t i = 0; i < f.size(); ++i) std::cout << i << " " << f[i] << '\n';
   }
 
+  std::string describe() const {
+    char buf[512];
+    check(fdb_upwind_describe(h_, buf, sizeof(buf)));
+    return buf;
+  }
   // binary dump of the field: row-major FP64, native byte order, no header
   void saveRaw(const std::string& filename) const {
     const std::vector<double> f = field();

@@ -99,6 +99,7 @@ int main(int argc, char** argv) {
       if (args.get<bool>("-timing")) {
         const double ms = up.lastGpuMilliseconds();
         const double updates = double(numCells[0]) * numCells[1] * numCells[2] * numTimeSteps;
+        std::cout << "kernel: " << up.describe() << '\n';
         std::cout << std::setprecision(17) << "check sum (17 digits): " << sum << '\n';
         if (doStd) std::cout << "std (17 digits): " << sd << '\n';
         std::cout << std::setprecision(6) << "gpu time [ms]: " << ms << "  GCUPS: " << updates / ms / 1e6

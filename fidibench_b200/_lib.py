@@ -83,6 +83,7 @@ _SIGS = {
     "fdb_upwind_get_slab": (i32, [vp, vp]),
     "fdb_upwind_set_kernel": (i32, [vp, i32]),
     "fdb_upwind_get_kernel": (i32, [vp, p_i32]),
+    "fdb_upwind_describe": (i32, [vp, C.c_char_p, C.c_size_t]),
     "fdb_upwind_set_fuse": (i32, [vp, i32]),
     "fdb_upwind_set_stream": (i32, [vp, vp]),
     "fdb_upwind_last_timing": (i32, [vp, p_dbl, p_dbl, p_dbl]),
@@ -106,6 +107,7 @@ _SIGS = {
     "fdb_stencil_get_kernel": (i32, [vp, p_i32]),
     "fdb_stencil_set_fuse": (i32, [vp, i32]),
     "fdb_stencil_get_fuse": (i32, [vp, p_i32]),
+    "fdb_stencil_describe": (i32, [vp, C.c_char_p, C.c_size_t]),
     "fdb_stencil_set_stream": (i32, [vp, vp]),
     "fdb_stencil_last_timing": (i32, [vp, p_dbl, p_dbl, p_dbl]),
     "fdb_stencil_destroy": (i32, [vp]),

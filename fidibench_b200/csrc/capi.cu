@@ -147,8 +147,10 @@ int timing_collect(Field* f) {
 int64_t upwind_mirrored_cell0(const fdb_upwind* h, const Geometry& g) {
   int64_t cell = 0;
   const int64_t stride[3] = {g.n[1] * g.n[2], g.n[2], 1};
+  // axis 0 is mirrored inside each slab: global plane 0 is the LAST device plane of the slab that owns it
+  const int64_t ext[3] = {g.n[0] / h->field.nparts, g.n[1], g.n[2]};
   for (int a = 0; a < 3; ++a)
-    if (h->flip[a]) cell += (g.n[a] - 1) * stride[a];
+    if (h->flip[a]) cell += (ext[a] - 1) * stride[a];
   return cell;
 }
 
@@ -179,32 +181,35 @@ int upwind_common_create(int ndims, const int64_t* numCells, const double* veloc
     if (!(lengths[j] > 0.0)) return set_error(FDB_E_INVALID, "lengths[%d] must be positive", j);
   fdb_upwind* h = new (std::nothrow) fdb_upwind();
   if (!h) return set_error(FDB_E_OOM, "out of host memory");
-  bool need_lo = false, need_hi = false;
   for (int j = 0; j < ndims; ++j) {
     h->velocity[j] = velocity[j];
     h->lengths[j] = lengths[j];
     h->num_cells[j] = numCells[j];
-    if (geo.axis_of[j] == 0 && geo.n[0] > 1) {
-      if (velocity[j] < 0.) need_hi = true; else need_lo = true;
-    }
   }
   // ghost depth: as many planes as the fused kernel may advance per sweep, slab permitting
   const int nparts = comm ? comm->nranks : (ngpus > 0 ? ngpus : 1);
   const int64_t nloc = geo.n[0] / nparts;
   const int G = (int)std::max<int64_t>(1, std::min<int64_t>(kMaxFuse, nloc));
-  // mirror the axes with a negative velocity when that lets the tiled kernels run (one slab, 3-D, the
-  // kernels' shape requirements); FDB_NO_FLIP=1 keeps the generic kernel for them
+  // Mirror the axes with a negative velocity when that lets the tiled kernels run (3-D, the kernels' shape
+  // requirements); FDB_NO_FLIP=1 keeps the generic kernel for them.  On several slabs every slab is mirrored in
+  // place: each device keeps its own global planes, reversed, and along axis 0 the ring then runs backwards.
   {
     const char* nf = getenv("FDB_NO_FLIP");
-    const bool allow = !(nf && *nf && atoi(nf) != 0) && nparts == 1 && ndims == 3 && geo.n[2] % 2 == 0 &&
-                       geo.n[2] >= 4 && geo.n[1] >= 2;
+    const bool allow = !(nf && *nf && atoi(nf) != 0) && ndims == 3 && geo.n[2] % 2 == 0 && geo.n[2] >= 4 && geo.n[1] >= 2;
     for (int j = 0; j < ndims && allow; ++j)
       if (velocity[j] < 0. && geo.n[geo.axis_of[j]] > 1) {
         h->flip[geo.axis_of[j]] = true;
         h->any_flip = true;
       }
   }
-  int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/1);
+  bool need_lo = false, need_hi = false;
+  for (int j = 0; j < ndims; ++j)
+    if (geo.axis_of[j] == 0 && geo.n[0] > 1) {
+      if (velocity[j] < 0. && !h->flip[0]) need_hi = true; else need_lo = true;
+    }
+  const bool reversed = h->flip[0] && nparts > 1;
+  int rc = field_create(&h->field, geo, G, need_lo, need_hi, ngpus, comm, /*want_tma=*/1, reversed);
+  h->field.planes_mirrored = h->flip[0];  // reductions report planes in global order
   if (rc == FDB_OK) rc = field_fill_delta(&h->field, 0, upwind_mirrored_cell0(h, geo));
   if (rc == FDB_OK) rc = field_sync(&h->field);
   if (rc != FDB_OK) {
@@ -529,6 +534,37 @@ int fdb_upwind_get_kernel(const fdb_upwind* h, int* kernel) {
   return FDB_OK;
 }
 
+int fdb_upwind_describe(const fdb_upwind* h, char* text, size_t capacity) {
+  if (!h || !text || capacity == 0) return set_error(FDB_E_INVALID, "null argument");
+  const Field& f = h->field;
+  UpwindCoeffs k;
+  upwind_coeffs(h, 1.0, &k);
+  int kern = FDB_KERNEL_GENERIC;
+  FDB_TRY(fdb_upwind_get_kernel(h, &kern));
+  const char* halo = f.single() ? "periodic alias (one slab)"
+                     : !f.direct ? (f.comm ? "NCCL send/recv ring" : "event-ordered peer copies")
+                     : f.push_stores ? "peer stores from the boundary kernel + stream counters" : "copy engines + stream counters";
+  if (kern == FDB_KERNEL_TMA) {
+    const int want = (h->fuse == 0) ? kAutoFuse : h->fuse;
+    const int fuse = (want > 1 && upwind_fused_supported(f, k, want)) ? want : 1;
+    if (fuse > 1)
+      snprintf(text, capacity, "upwind3d_fused_kernel<T=%d> (tile %s)%s; %d slab(s), halo: %s", fuse, upwind_fused_name(fuse),
+               h->any_flip ? ", field held mirrored along the axes with a negative velocity" : "", f.nparts, halo);
+    else
+      snprintf(text, capacity, "upwind3d_tma_kernel%s; %d slab(s), halo: %s", h->any_flip ? " (mirrored axes)" : "", f.nparts, halo);
+    return FDB_OK;
+  }
+  const char* why = h->kernel == FDB_KERNEL_GENERIC ? "asked for with fdb_upwind_set_kernel"
+                    : f.geo.ndims != 3              ? "the tiled kernels are 3-D"
+                    : (f.geo.n[2] % 2 != 0 || f.geo.n[2] < 4) ? "odd (or < 4) last extent: rows are not 16-byte aligned for TMA"
+                    : f.geo.n[1] < 2                ? "a single row per plane"
+                    : (k.up[0] != -1 || k.up[1] != -1 || k.up[2] != -1) ? "a negative velocity that was not mirrored (FDB_NO_FLIP)"
+                                                    : "no tiled configuration fits";
+  snprintf(text, capacity, "upwind_generic_kernel (one thread per cell, several times slower than the tiled kernels): %s; %d slab(s), halo: %s",
+           why, f.nparts, halo);
+  return FDB_OK;
+}
+
 int fdb_upwind_set_kernel(fdb_upwind* h, int kernel) {
   if (!h) return set_error(FDB_E_INVALID, "null handle");
   if (kernel != FDB_KERNEL_AUTO && kernel != FDB_KERNEL_GENERIC && kernel != FDB_KERNEL_TMA)
@@ -538,8 +574,7 @@ int fdb_upwind_set_kernel(fdb_upwind* h, int kernel) {
     upwind_coeffs(h, 1.0, &k);
     if (!upwind_tma_supported(h->field, k))
       return set_error(FDB_E_INVALID,
-                       "the TMA kernel needs a 3-D grid, an even last extent and -- on several slabs -- "
-                       "non-negative velocities");
+                       "the TMA kernel needs a 3-D grid and an even last extent");
   }
   h->kernel = kernel;
   return FDB_OK;
@@ -629,9 +664,7 @@ int fdb_upwind_plane_sums(fdb_upwind* h, double* sums, int64_t capacity, int64_t
   *count = g.n[0];
   if (!sums) return FDB_OK;  // size query
   if (capacity < g.n[0]) return set_error(FDB_E_INVALID, "room for %lld plane sums, %lld needed", (long long)capacity, (long long)g.n[0]);
-  FDB_TRY(field_plane_sums(&h->field, h->field.cur, sums));
-  if (h->flip[0]) std::reverse(sums, sums + g.n[0]);  // the device holds axis 0 mirrored
-  return FDB_OK;
+  return field_plane_sums(&h->field, h->field.cur, sums);  // already in global plane order
   FDB_GUARD_END
 }
 
@@ -803,6 +836,35 @@ int fdb_stencil_get_kernel(const fdb_stencil* h, int* kernel) {
   if (!h || !kernel) return set_error(FDB_E_INVALID, "null argument");
   const bool can = !h->br.ref_wrap && stencil_lap7_supported(h->field, h->br);
   *kernel = (h->kernel == FDB_KERNEL_GENERIC || !can) ? FDB_KERNEL_GENERIC : FDB_KERNEL_TMA;
+  return FDB_OK;
+}
+
+int fdb_stencil_describe(const fdb_stencil* h, char* text, size_t capacity) {
+  if (!h || !text || capacity == 0) return set_error(FDB_E_INVALID, "null argument");
+  const Field& f = h->field;
+  int kern = FDB_KERNEL_GENERIC, fuse = 1;
+  FDB_TRY(fdb_stencil_get_kernel(h, &kern));
+  FDB_TRY(fdb_stencil_get_fuse(h, &fuse));
+  if (kern == FDB_KERNEL_TMA) {
+    if (fuse == 2)
+      snprintf(text, capacity, "iterate: lap7_fused2_kernel (two applies per sweep, tile %s), apply: lap7_tma_kernel; %d slab(s)",
+               stencil_lap7_fused_name(f), f.nparts);
+    else
+      snprintf(text, capacity, "lap7_tma_kernel (one apply per sweep%s); %d slab(s)",
+               f.geo.ndims == 2 ? ", 2-D problem carried as one plane" : "", f.nparts);
+    return FDB_OK;
+  }
+  bool seven = h->br.nbranch <= 7;
+  for (int b = 0; b < h->br.nbranch && seven; ++b)
+    seven = std::abs(h->br.off[b][0]) + std::abs(h->br.off[b][1]) + std::abs(h->br.off[b][2]) <= 1;
+  const char* why = h->kernel == FDB_KERNEL_GENERIC ? "asked for with fdb_stencil_set_kernel"
+                    : h->br.ref_wrap                ? "reference index-wrap compatibility mode"
+                    : !seven                        ? "offsets beyond the radius-1 axis-aligned (7-point) set"
+                    : (f.geo.ndims == 1 || (f.geo.ndims == 2 && f.geo.n[0] != 1))
+                        ? "1-D, or a 2-D problem on several slabs: the tiled kernel needs whole planes"
+                        : "no tile (8/16/32 rows x 32/64/128 cells) divides the plane";
+  snprintf(text, capacity, "stencil_generic_kernel (one thread per cell, several times slower than the tiled kernels): %s; %d slab(s)",
+           why, f.nparts);
   return FDB_OK;
 }
 

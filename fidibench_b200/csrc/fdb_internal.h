@@ -133,6 +133,13 @@ struct Field {
   int nparts = 1;           // total slabs in the ring
   std::vector<Slab> slabs;
   int cur = 0;              // buf[cur] holds the current field
+  // The ring can run BACKWARDS along axis 0: a field held mirrored along that axis inside every slab (negative
+  // velocity along the slab axis, capi.cu) keeps each slab on the device that owns its global planes, so in device
+  // space the slab "after" part p is part p-1.  next_of / prev_of are the only places that know.
+  bool ring_reversed = false;
+  int next_of(int part) const { return ring_reversed ? (part + nparts - 1) % nparts : (part + 1) % nparts; }
+  int prev_of(int part) const { return ring_reversed ? (part + 1) % nparts : (part + nparts - 1) % nparts; }
+  bool planes_mirrored = false;  // device plane order inside a slab is the reverse of the global one (reductions)
   bool direct = true;       // halo transport: peer copies + stream flags (else NCCL / event-ordered copies)
   bool push_stores = true;  // direct transport: boundary kernels store into the neighbour's ghosts themselves
   uint64_t xseq = 0;        // halo exchanges issued so far (same on every rank)
@@ -152,7 +159,8 @@ struct Field {
 };
 
 int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_hi, int ngpus,
-                 fdb_comm* comm, int want_tma);  // want_tma: 0 none, 1 upwind, 2 7-point stencil
+                 fdb_comm* comm, int want_tma,  // want_tma: 0 none, 1 upwind, 2 7-point stencil
+                 bool ring_reversed = false);
 void field_destroy(Field* f);
 int field_set_stream(Field* f, void* stream);
 // async: no host synchronisation at all, the copy is ordered behind the handle's earlier work
@@ -163,8 +171,8 @@ int field_fill_delta(Field* f, int p, int64_t cell = 0);  // zero field, global 
 // (x[j] = HOST array of the extent of reference axis j); both publish buf[p] as the current field when `publish`
 int field_fill_random(Field* f, int p, uint64_t seed, bool publish);
 int field_fill_separable(Field* f, int p, int nd, const double* const* x_host, const int64_t* extents);
-// single-slab fields: buf[dst] = buf[src] mirrored along the flagged axes, on the main stream; buf[dst]
-// becomes the current field when `publish`
+// buf[dst] = buf[src] mirrored along the flagged axes INSIDE every slab, on the main streams; buf[dst] becomes the
+// current field when `publish`
 int field_mirror(Field* f, int src, int dst, const bool* flip, bool publish);
 // (re)fill the ghosts of buf[p] from the neighbours' boundary planes; enqueued on
 // the boundary streams, ev_ghost_ready[p] recorded.  `after_bnd` = wait for

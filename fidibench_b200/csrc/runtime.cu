@@ -9,6 +9,7 @@
 // of the field allocation.
 #include "fdb_internal.h"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -181,7 +182,7 @@ static int field_open_neighbours_ipc(Field* f) {
   if (local != FDB_OK) return local;
   for (int r = 0; r < n; ++r)
     if (all[(size_t)r].ok != 1.0) return set_error(FDB_E_CUDA, "rank %d could not export its buffers over CUDA IPC", r);
-  const int prev = (c->rank + n - 1) % n, next = (c->rank + 1) % n;
+  const int prev = f->prev_of(c->rank), next = f->next_of(c->rank);
   int opened = 0;
   auto open3 = [&](int rank, int side) -> int {
     void* p[3] = {nullptr, nullptr, nullptr};
@@ -223,7 +224,7 @@ int tma_encode_slab(Field* f, int d);       // kernels_tma.cu (upwind box shapes
 int tma_encode_slab_lap7(Field* f, int d);  // kernels_tma.cu (7-point stencil box shapes)
 
 int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_hi, int ngpus,
-                 fdb_comm* comm, int want_tma) {
+                 fdb_comm* comm, int want_tma, bool ring_reversed) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev < 1)
@@ -235,6 +236,8 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
   f->need_hi = need_hi;
   f->comm = comm;
   f->cur = 0;
+  f->ring_reversed = ring_reversed;
+  f->planes_mirrored = ring_reversed;
   if (comm) {
     ++comm->users;  // fdb_comm_destroy refuses while handles still use the communicator
     f->ngpus = 1;
@@ -301,7 +304,7 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
     const bool pretend_none = np && *np && atoi(np) != 0;
     for (int d = 0; d < f->ngpus; ++d) {
       FDB_CUDA(cudaSetDevice(f->slabs[d].device));
-      for (int o : {(d + 1) % f->ngpus, (d + f->ngpus - 1) % f->ngpus}) {
+      for (int o : {f->next_of(d), f->prev_of(d)}) {
         if (o == d) continue;
         int can = 0;
         FDB_CUDA(cudaDeviceCanAccessPeer(&can, f->slabs[d].device, f->slabs[o].device));
@@ -336,8 +339,8 @@ int field_create(Field* f, const Geometry& geo, int G, bool need_lo, bool need_h
       const int g = f->ngpus;
       for (int d = 0; d < g; ++d) {
         Slab& s = f->slabs[d];
-        const Slab& pv = f->slabs[(d + g - 1) % g];
-        const Slab& nx = f->slabs[(d + 1) % g];
+        const Slab& pv = f->slabs[f->prev_of(d)];
+        const Slab& nx = f->slabs[f->next_of(d)];
         for (int p = 0; p < 2; ++p) { s.nbr_buf[NBR_PREV][p] = pv.buf[p]; s.nbr_buf[NBR_NEXT][p] = nx.buf[p]; }
         s.nbr_flags[NBR_PREV] = pv.flags;
         s.nbr_flags[NBR_NEXT] = nx.flags;
@@ -523,10 +526,14 @@ int field_fill_separable(Field* f, int p, int nd, const double* const* x_host, c
 }
 
 int field_mirror(Field* f, int src, int dst, const bool* flip, bool publish) {
-  if (!f->single() || src == dst) return set_error(FDB_E_STATE, "mirroring needs a single-slab field and two buffers");
-  Slab& s = f->slabs[0];
-  FDB_CUDA(cudaSetDevice(s.device));
-  FDB_TRY(launch_mirror(f->body(0, src), f->body(0, dst), f->geo.n[0], f->geo.n[1], f->geo.n[2], flip, s.s_main));
+  if (src == dst) return set_error(FDB_E_STATE, "mirroring needs two buffers");
+  for (int d = 0; d < f->ngpus; ++d) {
+    Slab& s = f->slabs[d];
+    FDB_CUDA(cudaSetDevice(s.device));
+    // a host-driven overwrite of buf[dst]: the last halo exchange may still be reading its boundary planes
+    FDB_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_xchg_done, 0));
+    FDB_TRY(launch_mirror(f->body(d, src), f->body(d, dst), s.nloc(), f->geo.n[1], f->geo.n[2], flip, s.s_main));
+  }
   return publish ? field_publish(f, dst) : FDB_OK;
 }
 
@@ -574,7 +581,7 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
     FDB_CUDA(cudaSetDevice(s.device));
     // the planes to send are produced on s_bnd (after_bnd) or were published on s_main
     if (!after_bnd) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
-    const int next = (c->rank + 1) % c->nranks, prev = (c->rank + c->nranks - 1) % c->nranks;
+    const int next = f->next_of(c->rank), prev = f->prev_of(c->rank);
     double* top = f->body(0, p) + (s.nloc() - depth) * plane;
     double* bottom = f->body(0, p);
     FDB_NCCL(ncclGroupStart());
@@ -601,7 +608,7 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
     // last sweep is (ev_local_done as recorded at the end of that sweep)
     FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, s.ev_local_done, 0));
     if (f->need_lo) {
-      const int src = (d + g - 1) % g;
+      const int src = f->prev_of(d);
       Slab& o = f->slabs[src];
       FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, after_bnd ? o.ev_bnd_done : o.ev_local_done, 0));
       FDB_CUDA(cudaMemcpyPeerAsync(f->ghost_lo(d, p) + lo_skip, s.device,
@@ -609,7 +616,7 @@ int field_exchange(Field* f, int p, bool after_bnd, int depth) {
                                    s.s_bnd));
     }
     if (f->need_hi) {
-      const int src = (d + 1) % g;
+      const int src = f->next_of(d);
       Slab& o = f->slabs[src];
       FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, after_bnd ? o.ev_bnd_done : o.ev_local_done, 0));
       FDB_CUDA(cudaMemcpyPeerAsync(f->ghost_hi(d, p), s.device, f->body(src, p), o.device, bytes,
@@ -730,8 +737,8 @@ static int field_sweep_legacy(Field* f, SweepLauncher* L, int depth) {
       // WAR on the planes about to be rewritten: the neighbours' last pull of them (two
       // sweeps ago, same buffer) must have finished.  NCCL sends are ordered by s_bnd itself.
       const int g = f->ngpus;
-      if (f->need_lo) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[(d + 1) % g].ev_ghost_ready[Y], 0));
-      if (f->need_hi) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[(d + g - 1) % g].ev_ghost_ready[Y], 0));
+      if (f->need_lo) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[f->next_of(d)].ev_ghost_ready[Y], 0));
+      if (f->need_hi) FDB_CUDA(cudaStreamWaitEvent(s.s_bnd, f->slabs[f->prev_of(d)].ev_ghost_ready[Y], 0));
     }
     FDB_TRY(L->launch(f, d, X, depth, 0, b_end, s.s_bnd));
     FDB_TRY(L->launch(f, d, X, depth, t_beg, s.nloc(), s.s_bnd));
@@ -917,6 +924,10 @@ static int field_reduce(Field* f, int p, int mode, double mean, double* out, dou
       FDB_CUDA(cudaSetDevice(s.device));
       FDB_CUDA(cudaStreamSynchronize(s.s_main));
     }
+  }
+  if (f->planes_mirrored) {  // device order inside a slab is the reverse of the global plane order
+    const int64_t nl = n0 / f->nparts;
+    for (int64_t b = 0; b < n0; b += nl) std::reverse(sums.begin() + b, sums.begin() + b + nl);
   }
   double acc = 0.0;
   for (int64_t i = 0; i < n0; ++i) acc += sums[(size_t)i];  // global plane order

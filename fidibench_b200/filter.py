@@ -189,6 +189,12 @@ class Filter:
         """Reproduce Filter.cpp:240's (int %= size_t) wrap (non-periodic unless the extent is a power of two)."""
         check(lib.fdb_stencil_set_ref_wrap(self._h, 1 if on else 0))
 
+    def describe(self) -> str:
+        """Which kernel runs and, for the generic one, why the tiled kernels do not apply."""
+        buf = C.create_string_buffer(512)
+        check(lib.fdb_stencil_describe(self._h, buf, 512))
+        return buf.value.decode()
+
     def set_kernel(self, kernel: int) -> None:
         check(lib.fdb_stencil_set_kernel(self._h, int(kernel)))
 

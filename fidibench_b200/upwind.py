@@ -151,6 +151,12 @@ class Upwind:
     def sync(self) -> None:
         check(lib.fdb_upwind_sync(self._h))
 
+    def describe(self) -> str:
+        """Which kernel runs and, for the generic one, why the tiled kernels do not apply."""
+        buf = C.create_string_buffer(512)
+        check(lib.fdb_upwind_describe(self._h, buf, 512))
+        return buf.value.decode()
+
     def set_kernel(self, kernel: int) -> None:
         check(lib.fdb_upwind_set_kernel(self._h, int(kernel)))
 

@@ -156,6 +156,9 @@ int fdb_upwind_get_slab(fdb_upwind *h, double *host_slab);
 int fdb_upwind_set_kernel(fdb_upwind *h, int kernel);
 /* which kernel the next advect will use (FDB_KERNEL_GENERIC or FDB_KERNEL_TMA) */
 int fdb_upwind_get_kernel(const fdb_upwind *h, int *kernel);
+/* one line of text: which kernel the next advect launches (and, for the slow generic kernel, WHY the tiled ones do
+ * not apply), how many slabs, which halo transport */
+int fdb_upwind_describe(const fdb_upwind *h, char *text, size_t capacity);
 /* time steps fused per sweep by the TMA kernel (temporal blocking): 1..4, or 0 = auto
  * (the default: the fastest setting the problem supports).  Results do not depend on it. */
 int fdb_upwind_set_fuse(fdb_upwind *h, int steps_per_sweep);
@@ -223,6 +226,8 @@ int fdb_stencil_get_slab(fdb_stencil *h, int which, double *host_slab);
 int fdb_stencil_set_ref_wrap(fdb_stencil *h, int on);
 int fdb_stencil_set_kernel(fdb_stencil *h, int kernel);
 int fdb_stencil_get_kernel(const fdb_stencil *h, int *kernel);
+/* one line of text: the kernels apply / iterate launch, or why only the generic kernel applies */
+int fdb_stencil_describe(const fdb_stencil *h, char *text, size_t capacity);
 int fdb_stencil_set_stream(fdb_stencil *h, void *cuda_stream);
 int fdb_stencil_last_timing(const fdb_stencil *h, double *gpu_ms, double *cell_updates,
                             double *halo_bytes);

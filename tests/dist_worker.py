@@ -184,9 +184,14 @@ def gpu_main():
 
     # negative velocity along the slab axis: ghost plane above
     up = fb.Upwind([-1.0, 1.0, 1.0], [1.0] * 3, a.shape, comm=comm)
+    assert up.kernel() == fb.FDB_KERNEL_TMA, up.describe()   # mirrored in place, the ring runs backwards
     up.set_field(a)
     up.advect(7, 0.1 / a.shape[1])
     assert np.array_equal(up.slab(), oracle.c.upwind_advect(a, 7, velocity=[-1, 1, 1], dt=0.1 / a.shape[1])[up.lo:up.hi])
+    with fb.Upwind([-1.0, 1.0, 1.0], [1.0] * 3, a.shape) as single:
+        single.set_field(a)
+        single.advect(7, 0.1 / a.shape[1])
+        assert single.checksum() == up.checksum(), "checksum of a mirrored field is not partition-invariant"
     up.close()
 
     # delta on the last plane of slab 0 (SURVEY.md T1 ii)
