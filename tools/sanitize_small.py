@@ -11,7 +11,8 @@ import oracle  # noqa: E402
 
 rng = np.random.default_rng(5)
 a = rng.random((7, 40, 132))
-for fuse in (1, 2, 3, 4):
+FUSES = [int(x) for x in os.environ.get("SAN_FUSES", "1,2,3,4").split(",") if x]
+for fuse in FUSES:
     with fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as up:
         up.set_fuse(fuse)
         up.set_field(a)
