@@ -35,9 +35,12 @@ class Cfg:
 
 
 def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, ibeg: int, iend: int,
-                out: np.ndarray) -> None:
+                out: np.ndarray, split: bool = False, reverse: bool = False) -> None:
     """One launch on the slab [lo,hi) of the periodic field x: local output planes [ibeg,iend) of `out`
-    receive the field T time steps later.  c = (c0, c1, c2)."""
+    receive the field T time steps later.  c = (c0, c1, c2).
+    split: the lean formulation's exchange-tile layout (Lean<C, PUSH, SPLIT = true>): even cells (x) and odd cells
+    (y) of a tile row in two halves of the row, 8 bytes per thread, and only what a neighbour reads is stored
+    (every row's y, the last row's x).  reverse: chunks walked top chunk first (single-launch ring sweeps)."""
     C = cfg
     T = C.T
     n0, n1, n2 = x.shape
@@ -53,6 +56,9 @@ def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, i
     P = C.PITCH
     xt = q0 * P + (C.LEFT + 2 * tx) * 8
     tb = xt + (C.HR - T) * P
+    xs = q0 * P + 8 + tx * 8          # split layout: row above the thread's first row, x half, this thread's slot
+    YOFF = P // 2
+    assert not split or (C.TX + 1) * 8 <= YOFF
     rowmask = [(q0 + r >= T - 1) for r in range(C.R)]
 
     def cell(ctr, im1, jm1, km1):
@@ -79,6 +85,8 @@ def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, i
         kt = wi % nkt
         jt = (wi // nkt) % njt
         ic = wi // (nkt * njt)
+        if reverse:
+            ic = nchunk - 1 - ic
         i0 = ibeg + ic * ci
         i1 = min(i0 + ci, iend)
         kb = kt * C.BK - 8
@@ -131,10 +139,18 @@ def fused_steps(x: np.ndarray, c, lo: int, hi: int, G: int, cfg: Cfg, ci: int, i
                     xb = xbuf[xsel]
                     xsel ^= 1
                     xb[:] = np.nan
-                    for r in range(C.R):
-                        ad = (xt + (1 + r) * P) // 8
-                        xb[ad], xb[ad + 1] = nv[r, :, 0], nv[r, :, 1]
-                    up = lds_v2(xb, xt)
-                    for r in range(C.R):
-                        km[r] = lds_f64(xb, xt + (1 + r) * P - 8)
+                    if split:
+                        for r in range(C.R):
+                            xb[(xs + (1 + r) * P + YOFF) // 8] = nv[r, :, 1]
+                        xb[(xs + C.R * P) // 8] = nv[C.R - 1, :, 0]
+                        up = np.stack([lds_f64(xb, xs), lds_f64(xb, xs + YOFF)], axis=-1)
+                        for r in range(C.R):
+                            km[r] = lds_f64(xb, xs + (1 + r) * P + YOFF - 8)
+                    else:
+                        for r in range(C.R):
+                            ad = (xt + (1 + r) * P) // 8
+                            xb[ad], xb[ad + 1] = nv[r, :, 0], nv[r, :, 1]
+                        up = lds_v2(xb, xt)
+                        for r in range(C.R):
+                            km[r] = lds_f64(xb, xt + (1 + r) * P - 8)
                     v = nv

@@ -59,9 +59,12 @@ def tma_box(smem: np.ndarray, dst: int, tensor: np.ndarray, c0: int, c1: int, c2
 
 
 def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: int, ibeg: int, iend: int,
-                      out: np.ndarray, unit: bool = False, shfl: bool = False) -> None:
+                      out: np.ndarray, unit: bool = False, shfl: bool = False, lean: bool = False) -> None:
     """One launch of the kernel on the slab [lo,hi) of the periodic field x: writes local output
-    planes [ibeg,iend) of `out` (shape of the slab).  Ghost tensors hold G planes each."""
+    planes [ibeg,iend) of `out` (shape of the slab).  Ghost tensors hold G planes each.
+    lean: lap7_fused2_lean_kernel -- the exchange tile keeps even cells (x) and odd cells (y) of a row in two halves
+    (8 bytes per thread), and the register sets are NOT reset between work items: here they are poisoned with NaN at
+    every item start, so a stale value reaching a stored cell fails the comparison."""
     C = cfg
     n0, n1, n2 = x.shape
     nloc = hi - lo
@@ -79,6 +82,9 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
     q0 = ty * C.R
     tb = q0 * C.PITCH + 16 + tx * 16
     P = C.PITCH
+    xs = q0 * P + 8 + tx * 8   # lean: row above the thread's first row, x half, this thread's slot
+    YOFF = P // 2
+    assert not lean or (C.TX + 2) * 8 <= YOFF
     rowmask = [(q0 + r >= 1) & (q0 + r <= C.CJ - 2) for r in range(C.R)]
     store_cols = (tx >= 1) & (tx <= C.TX - 2)
     # SHFL variant: the k-1 / k+1 cells come from the adjacent LANE's registers except at a warp's edge
@@ -126,7 +132,7 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
         first_k, last_k = kt == 0, kt == nkt - 1
         k = kt * C.BK - 2 + 2 * tx
         j = jt * C.BJ - 1 + q0
-        z = np.zeros((C.R, C.WORKERS, 2))
+        z = np.full((C.R, C.WORKERS, 2), np.nan) if lean else np.zeros((C.R, C.WORKERS, 2))
         below0, part1, below1, part2 = z.copy(), z.copy(), z.copy(), z.copy()
         for p in range(i0 - 2, i1 + 2):
             # ---- loader warp: TMA boxes, then the wrap columns copied into the tile rows
@@ -186,9 +192,13 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
             xsel ^= 1
             xb[:] = np.nan
             for r in range(C.R):
-                ad = (tb + (1 + r) * P) // 8
-                xb[ad] = l1[r, :, 0]
-                xb[ad + 1] = l1[r, :, 1]
+                if lean:
+                    xb[(xs + (1 + r) * P) // 8] = l1[r, :, 0]
+                    xb[(xs + (1 + r) * P + YOFF) // 8] = l1[r, :, 1]
+                else:
+                    ad = (tb + (1 + r) * P) // 8
+                    xb[ad] = l1[r, :, 0]
+                    xb[ad + 1] = l1[r, :, 1]
             for r in range(C.R):
                 jm = up if r == 0 else c[r - 1]
                 jp = dn if r == C.R - 1 else c[r + 1]
@@ -201,10 +211,17 @@ def fused_two_applies(x: np.ndarray, w, lo: int, hi: int, G: int, cfg: Cfg, ci: 
                 part1[r, :, 0], part1[r, :, 1] = xx, yy
             below0 = c.copy()
             # named barrier
-            up1 = lds_v2(xb, tb)
-            dn1 = lds_v2(xb, tb + (C.R + 1) * P)
-            for r in range(C.R):
-                km[r], kp[r] = nbr_cells(l1[r], lds_f64(xb, tb + (1 + r) * P - 8), lds_f64(xb, tb + (1 + r) * P + 16))
+            if lean:
+                up1 = np.stack([lds_f64(xb, xs), lds_f64(xb, xs + YOFF)], axis=-1)
+                dn1 = np.stack([lds_f64(xb, xs + (C.R + 1) * P), lds_f64(xb, xs + (C.R + 1) * P + YOFF)], axis=-1)
+                for r in range(C.R):
+                    km[r] = lds_f64(xb, xs + (1 + r) * P + YOFF - 8)   # y of the thread to the left
+                    kp[r] = lds_f64(xb, xs + (1 + r) * P + 8)          # x of the thread to the right
+            else:
+                up1 = lds_v2(xb, tb)
+                dn1 = lds_v2(xb, tb + (C.R + 1) * P)
+                for r in range(C.R):
+                    km[r], kp[r] = nbr_cells(l1[r], lds_f64(xb, tb + (1 + r) * P - 8), lds_f64(xb, tb + (1 + r) * P + 16))
             for r in range(C.R):
                 jm = up1 if r == 0 else l1[r - 1]
                 jp = dn1 if r == C.R - 1 else l1[r + 1]

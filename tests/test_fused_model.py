@@ -20,14 +20,17 @@ SEED = 20261017
     (3, 18, 3, 64, (4, 20, 200), 4),     # 64-cell tiles
     (3, 24, 8, 128, (3, 48, 128), 3),
 ])
-def test_model_single_slab(T, CJ, R, BK, shape, ci):
+@pytest.mark.parametrize("split", [False, True])
+def test_model_single_slab(T, CJ, R, BK, shape, ci, split):
+    """split = the exchange-tile layout of the lean formulation (the default kernel for T >= 3), with the chunks walked
+    top chunk first as the single-launch ring sweeps do."""
     rng = np.random.default_rng(SEED)
     x = rng.random(shape)
     out = np.full(shape, np.nan)
     # the driver's dt and the engine's coefficients ((dt*v)*up)/dx, ref: upwind.cxx:72,186-192
     dt = oracle.c.upwind_dt(shape, [1.0] * 3, [1.0] * 3)
     c = [((dt * 1.0) * -1) / (1.0 / shape[j]) for j in range(3)]
-    fused_steps(x, c, 0, shape[0], T, Cfg(T, CJ, R, BK), ci, 0, shape[0], out)
+    fused_steps(x, c, 0, shape[0], T, Cfg(T, CJ, R, BK), ci, 0, shape[0], out, split=split, reverse=split)
     assert np.array_equal(out, oracle.c.upwind_advect(x, T))
 
 

@@ -25,12 +25,14 @@ def two_applies(x, w):
     ((2, 32, 128), 16, 2, 2),     # thinnest slab
 ])
 @pytest.mark.parametrize("unit", [False, True])
-def test_model_single_slab(shape, BJ, R, ci, unit):
+@pytest.mark.parametrize("lean", [False, True])
+def test_model_single_slab(shape, BJ, R, ci, unit, lean):
+    """lean = lap7_fused2_lean_kernel (the default): split exchange tile, register sets never reset between items."""
     rng = np.random.default_rng(SEED)
     x = rng.random(shape) - 0.5
     w = [1.0, 1.0, 1.0, -6.0, 1.0, 1.0, 1.0]
     out = np.full(shape, np.nan)
-    fused_two_applies(x, w, 0, shape[0], 2, Cfg(BJ, R), ci, 0, shape[0], out, unit=unit)
+    fused_two_applies(x, w, 0, shape[0], 2, Cfg(BJ, R), ci, 0, shape[0], out, unit=unit, lean=lean)
     assert np.array_equal(out, two_applies(x, w))
 
 
@@ -65,6 +67,10 @@ def test_model_slab_of_a_ring_with_boundary_split():
     out = np.full((hi - lo, 16, 128), np.nan)
     for ibeg, iend in ((0, 2), (2, 4)):
         fused_two_applies(x, w, lo, hi, 2, Cfg(16, 3), 64, ibeg, iend, out)
+    assert np.array_equal(out, ref[lo:hi])
+    out = np.full((hi - lo, 16, 128), np.nan)
+    for ibeg, iend in ((0, 2), (2, 4)):
+        fused_two_applies(x, w, lo, hi, 2, Cfg(16, 3), 64, ibeg, iend, out, lean=True)
     assert np.array_equal(out, ref[lo:hi])
     # ghost tensors deeper than the sweep (G = 3): the planes nearest the body are the ones read
     out = np.full((hi - lo, 16, 128), np.nan)
