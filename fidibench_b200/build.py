@@ -27,6 +27,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # the kernels use __d*_rn intrinsics as well, this is the belt to those braces.
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "--fmad=false", "-Xcompiler", "-fPIC,-O2",
                      "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+# experiments only (e.g. FDB_NVCC_EXTRA=-DFDB_DBG_NO_LANDED_WAIT for the synccheck probe of profiles/r02s_*)
+NVCC_FLAGS += [f for f in os.environ.get("FDB_NVCC_EXTRA", "").split() if f]
 
 
 def nvcc() -> str:

@@ -310,8 +310,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 
     for (int64_t p = i0 - C::T; p < i1; ++p) {
       ooff += plane;
-      mbar_wait(full + 8 * stage, phase);
-      mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
+      mbar_wait(full + 8 * stage, phase);  // the loader's hand-over (see Lean::step)
       const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
       double2 v[C::R];
       double km[C::R];
@@ -393,7 +392,7 @@ struct Lean {
 
   struct State {
     uint32_t st;      // this thread's base inside the current stage
-    uint32_t bar;     // `full` barrier of the current stage (landed = bar - 8*STAGES, empty = bar + 8*STAGES)
+    uint32_t bar;     // `full` barrier of the current stage (empty = bar + 8*STAGES)
     uint32_t par;     // phase parity of the current round over the stages
     uint32_t st0, bar0, bar_end;
     uint32_t xt0, xt1;  // this thread's base inside the two exchange tiles
@@ -401,19 +400,19 @@ struct Lean {
     double* orow[C::R];   // output rows of the plane being computed
     int64_t plane_elems;
     int64_t peer_delta;   // PUSH: byte distance to the same cell in the next slab's ghost planes
-    uint32_t smask;       // rows x columns this thread stores; bit 31: the item is a first k-tile
+    uint32_t smask;       // rows x columns this thread stores
     int lane;
   };
-  static constexpr uint32_t kFirstK = 0x80000000u;
 
   // one plane: level 0 comes from the stage, level s+1 from level s of this plane (X) and of the previous one (Pv)
   template <int PARITY>
   static __device__ __forceinline__ void step(State& z, double2 (&Pv)[C::T][C::R], double2 (&X)[C::T][C::R], bool store,
                                               bool push) {
-    // the TMA bytes of the stage have landed; only the first k-tile also waits for the loader warp's hand-over
-    // (its wrap columns are patched in after landing -- other tiles are complete as they land)
-    mbar_wait(z.bar - 8 * C::STAGES, z.par);
-    if (z.smask & kFirstK) mbar_wait(z.bar, z.par);
+    // the loader warp hands the stage over once its TMA bytes have landed (it waits on `landed`, an acquire) and the wrap
+    // columns are patched: its arrive on `full` (release) / this wait (acquire) order the TMA writes before the loads
+    // below.  The consumers used to wait on `landed` as well; the hand-over already implies it, and compute-sanitizer's
+    // synccheck reports a transaction barrier that two groups of threads wait on ("Missing init", profiles/r02s_*).
+    mbar_wait(z.bar, z.par);
     double km[R];
     double2 up = lds_v2(z.st);
 #pragma unroll
@@ -541,7 +540,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
     const int64_t k = (int64_t)kt * C::BK - C::HKC + 2 * tx;
     const int64_t j = (int64_t)jt * C::BJ - (C::T - 1) + q0;
     z.smask = (2 * tx >= C::HKC && k < a.n2) ? rowmask : 0u;
-    if (kt == 0) z.smask |= L::kFirstK;
 #pragma unroll
     for (int r = 0; r < C::R; ++r) {
       if (j + r >= a.n1) z.smask &= ~(1u << r);

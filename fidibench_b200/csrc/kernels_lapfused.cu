@@ -286,8 +286,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB)
 
     for (int64_t p = i0 - 2; p <= i1 + 1; ++p) {
       ooff += plane;
-      mbar_wait(full + 8 * stage, phase);
-      mbar_wait(landed + 8 * stage, phase);  // already complete: orders this thread behind the TMA writes
+      mbar_wait(full + 8 * stage, phase);  // the loader's hand-over: TMA bytes landed, wrap columns patched
       const uint32_t sb = smem + stage * C::STAGE_BYTES + tb;
       double2 c[C::R];
       double km[C::R], kp[C::R];
@@ -418,8 +417,9 @@ struct LapLean {
                                               double2 (&Lp)[C::R], double2 (&Lc)[C::R], double2 (&part1)[C::R],
                                               double2 (&part2)[C::R], bool store) {
     const double w0 = a.w[0], w1 = a.w[1], w2 = a.w[2], w3 = a.w[3], w4 = a.w[4], w5 = a.w[5], w6 = a.w[6];
-    mbar_wait(z.bar - 8 * C::STAGES, z.par);  // the TMA bytes have landed
-    mbar_wait(z.bar, z.par);                  // ... and the loader warp has patched the wrap columns
+    // the loader warp's hand-over: it waited for the TMA bytes (acquire on `landed`), patched the wrap columns and
+    // arrived on `full` (release); this acquire orders all of it before the loads below (see kernels_fused.cu)
+    mbar_wait(z.bar, z.par);
     double km[R], kp[R];
     const double2 up = lds_v2(z.st);
     const double2 dn = lds_v2(z.st + (R + 1) * P);

@@ -51,6 +51,9 @@ for weights in (w, rng.standard_normal(7)):
         for _ in range(3):
             r = oracle.c.stencil_apply(r, off, weights)
         assert np.array_equal(fl.get(), r)
+if os.environ.get("SAN_SKIP_MIRROR"):
+    print("sanitize_small ok (without the mirrored upwind case)")
+    sys.exit(0)
 # negative velocities on the mirrored grid (mirror_kernel + tiled kernels)
 c = rng.random((6, 10, 36))
 with fb.Upwind([-1.0, 1.0, -0.5], [1.0] * 3, c.shape) as up:
