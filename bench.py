@@ -476,10 +476,12 @@ def parity_block(ctx, up_bench, dt_bench, slab_bytes):
 
 
 def upwind_kernel_name(fb, up, fuse):
+    """The __global__ function the sweeps launch, as ncu lists it (from fdb_upwind_describe), and steps per launch."""
     if up.kernel() != fb.FDB_KERNEL_TMA:
         return "upwind_generic_kernel", 1
-    f = fuse or 3
-    return ("upwind3d_tma_kernel" if f == 1 else f"upwind3d_fused_kernel<T={f}>"), f
+    name = up.describe().split(" ")[0]          # e.g. upwind3d_fused_lean_kernel<T=3>
+    f = int(name.split("T=")[1].rstrip(">")) if "T=" in name else 1
+    return name, f
 
 
 def time_upwind(ctx, up, T, steps, warmup, dt, sampler=None):
@@ -562,7 +564,7 @@ def laplacian_entry(ctx, dims, steps, warmup, fuse=0, kernel="auto", sampler=Non
         fl.set_fuse(fuse)
     fz = fl.fuse()
     tiled = fl.kernel() == fb.FDB_KERNEL_TMA
-    name = "stencil_generic_kernel" if not tiled else ("lap7_fused2_kernel" if fz == 2 else "lap7_tma_kernel")
+    name = "stencil_generic_kernel" if not tiled else (fl.describe().split(" ")[1] if fz == 2 else "lap7_tma_kernel")
     nloc = fl.hi - fl.lo
     total = float(np.prod(dims))
     slab_cells = int(total) // dims[0] * nloc

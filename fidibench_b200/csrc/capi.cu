@@ -97,7 +97,9 @@ struct StencilSweep : SweepLauncher {
   }
 };
 
-constexpr int kAutoFuse = 3;  // round-1 sweeps: T=3 is the fastest bit-exact setting (profiles/)
+// Sustained runs (bench.py, power-capped; profiles/r02zz_*): T = 4 sweeps are 2.6-3.4 % ahead of T = 3 at 1 and 2 GPUs
+// (25 % less DRAM traffic per step, and 100 steps are 25 x 4 with no remainder); short bursts at 512^3 favour T = 3.
+constexpr int kAutoFuse = 4;
 
 // ref: upwind.cxx:34-36,72 -- upDirection, deltas and the per-axis coefficient
 // ((deltaTime * v[j]) * upDirection[j]) / deltas[j], evaluated left to right.
@@ -548,7 +550,7 @@ int fdb_upwind_describe(const fdb_upwind* h, char* text, size_t capacity) {
     const int want = (h->fuse == 0) ? kAutoFuse : h->fuse;
     const int fuse = (want > 1 && upwind_fused_supported(f, k, want)) ? want : 1;
     if (fuse > 1)
-      snprintf(text, capacity, "upwind3d_fused_kernel<T=%d> (tile %s)%s; %d slab(s), halo: %s", fuse, upwind_fused_name(fuse),
+      snprintf(text, capacity, "%s<T=%d> (tile %s)%s; %d slab(s), halo: %s", upwind_fused_kernel_name(fuse), fuse, upwind_fused_name(fuse),
                h->any_flip ? ", field held mirrored along the axes with a negative velocity" : "", f.nparts, halo);
     else
       snprintf(text, capacity, "upwind3d_tma_kernel%s; %d slab(s), halo: %s", h->any_flip ? " (mirrored axes)" : "", f.nparts, halo);
@@ -625,11 +627,17 @@ int fdb_upwind_advect_async(fdb_upwind* h, int64_t numTimeSteps, double deltaTim
     depths.push_back(t);
     done += t;
   }
-  // a plan ending in [3, 1] runs as [2, 2]: the single-step kernel is the slowest per time step
-  if (depths.size() >= 2 && depths.back() == 1 && depths[depths.size() - 2] == 3 &&
-      upwind_fused_supported(*f, sw.k, 2)) {
-    depths[depths.size() - 2] = 2;
-    depths.back() = 2;
+  // a plan ending in [3, 1] runs as [2, 2], one ending in [4, 1] as [3, 2]: the single-step kernel is the slowest per
+  // time step (depths still never increase along the plan)
+  if (depths.size() >= 2 && depths.back() == 1) {
+    const int before = depths[depths.size() - 2];
+    if (before == 3 && upwind_fused_supported(*f, sw.k, 2)) {
+      depths[depths.size() - 2] = 2;
+      depths.back() = 2;
+    } else if (before == 4 && upwind_fused_supported(*f, sw.k, 3) && upwind_fused_supported(*f, sw.k, 2)) {
+      depths[depths.size() - 2] = 3;
+      depths.back() = 2;
+    }
   }
   FDB_TRY(timing_begin(f));
   FDB_TRY(field_run_sweeps(f, &sw, depths.data(), (int)depths.size()));
@@ -848,8 +856,8 @@ int fdb_stencil_describe(const fdb_stencil* h, char* text, size_t capacity) {
   FDB_TRY(fdb_stencil_get_fuse(h, &fuse));
   if (kern == FDB_KERNEL_TMA) {
     if (fuse == 2)
-      snprintf(text, capacity, "iterate: lap7_fused2_kernel (two applies per sweep, tile %s), apply: lap7_tma_kernel; %d slab(s)",
-               stencil_lap7_fused_name(f), f.nparts);
+      snprintf(text, capacity, "iterate: %s (two applies per sweep, tile %s), apply: lap7_tma_kernel; %d slab(s)",
+               stencil_lap7_fused_kernel_name(), stencil_lap7_fused_name(f), f.nparts);
     else
       snprintf(text, capacity, "lap7_tma_kernel (one apply per sweep%s); %d slab(s)",
                f.geo.ndims == 2 ? ", 2-D problem carried as one plane" : "", f.nparts);

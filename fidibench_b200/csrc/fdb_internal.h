@@ -249,6 +249,7 @@ bool upwind_fused_supported(const Field& f, const UpwindCoeffs& k, int T);
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,
                         cudaStream_t s, double* peer_out = nullptr, int64_t peer_from = 0, const HaloSignal* sig = nullptr);
 bool upwind_fused_can_signal(int T);
+const char* upwind_fused_kernel_name(int T);
 int upwind_fused_prepare(Field& f, int d, int T);
 int upwind_tma_prepare(const Field& f, int d);
 int stencil_lap7_prepare(const Field& f, int d);
@@ -274,6 +275,7 @@ bool stencil_lap7_fused_supported(const Field& f, const StencilBranches& b);
 int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend, const StencilBranches& b,
                               cudaStream_t s);
 const char* stencil_lap7_fused_name(const Field& f);
+const char* stencil_lap7_fused_kernel_name();
 int stencil_lap7_fused_prepare(Field& f, int d, const StencilBranches& b);
 
 int launch_plane_sums(const double* body, int64_t nloc, int64_t plane, int mode, double mean,

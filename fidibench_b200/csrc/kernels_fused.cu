@@ -726,6 +726,11 @@ int upwind_fused_prepare(Field& f, int d, int T) {
   return FDB_OK;
 }
 
+// the __global__ function a sweep of T steps launches (what ncu lists)
+const char* upwind_fused_kernel_name(int T) {
+  return fz_env_int("FDB_FUSED_IMPL", fz_default_impl(T)) == 1 ? "upwind3d_fused_kernel" : "upwind3d_fused_lean_kernel";
+}
+
 bool upwind_fused_can_signal(int T) { return fz_env_int("FDB_FUSED_IMPL", fz_default_impl(T)) != 1; }
 
 int launch_upwind_fused(Field& f, int d, int X, int T, int64_t ibeg, int64_t iend, const UpwindCoeffs& k,

@@ -776,6 +776,10 @@ int launch_stencil_lap7_fused(Field& f, int d, int X, int64_t ibeg, int64_t iend
   return FDB_OK;
 }
 
+const char* stencil_lap7_fused_kernel_name() {
+  return lf_env_int("FDB_LAPF_IMPL", kDefaultLapFusedImpl) == 2 ? "lap7_fused2_lean_kernel" : "lap7_fused2_kernel";
+}
+
 const char* stencil_lap7_fused_name(const Field& f) {
   const LapFusedConfig* C = lapf_pick(f);
   return C ? C->name : "";

@@ -58,7 +58,7 @@ def test_fresh_line_from_the_code_under_test(gpu_fb):
     e = j["e2e"]
     assert e["h2d_bytes_per_step"] == 8 * 512 ** 3 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < j["value"]
     assert e["with_field_copyback"]["d2h_bytes_per_step"] == 8 * 512 ** 3
-    assert j["gpu_launches"] >= 3 * 34
+    assert j["gpu_launches"] >= 3 * 25   # 100 time steps = 25 sweeps of 4
     a = j["also"]["upwind128"]
     assert a["value"] > 0 and a["roofline"]["frac"] > 0 and a["time_steps_per_step"] == 10
 
@@ -81,7 +81,7 @@ def test_recorded_b200_laplacian_line_and_its_reference_arm():
     for k in REQUIRED:
         assert k in j, k
     assert j["unit"] == "GCUPS" and j["dtype"] == "f64" and "laplacian" in j["metric"]
-    assert j["config"]["kernel"] == "lap7_fused2_kernel" and j["config"]["applies_per_sweep"] == 2
+    assert j["config"]["kernel"].startswith("lap7_fused2") and j["config"]["applies_per_sweep"] == 2
     r = j["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
     assert j["e2e"]["h2d_bytes_per_step"] == 8 * 1024 ** 3 and j["e2e"]["value"] < j["value"]

@@ -384,7 +384,7 @@ def test_negative_velocities_on_slab_rings_run_the_tiled_kernels(gpu_fb, ngpus, 
     a = rng.random((16 * ngpus, 40, 132))
     dt = C.upwind_dt(a.shape, [abs(v) for v in vel], [1.0] * 3)
     with gpu_fb.Upwind(list(vel), [1.0] * 3, a.shape, ngpus=ngpus) as up:
-        assert up.kernel() == gpu_fb.FDB_KERNEL_TMA and "upwind3d_fused_kernel" in up.describe() and "mirrored" in up.describe()
+        assert up.kernel() == gpu_fb.FDB_KERNEL_TMA and "upwind3d_fused" in up.describe() and "mirrored" in up.describe()
         assert up.default_dt() == dt
         up.set_field(a)
         for n in (7, 3, 5):
@@ -410,7 +410,7 @@ def test_negative_velocities_on_slab_rings_run_the_tiled_kernels(gpu_fb, ngpus, 
 
 def test_describe_names_the_kernel_and_the_reason_for_the_generic_one(gpu_fb):
     with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, (16, 16, 64)) as up:
-        assert up.describe().startswith("upwind3d_fused_kernel<T=3>")
+        assert up.describe().startswith("upwind3d_fused_lean_kernel<T=4>")
         up.set_fuse(1)
         assert up.describe().startswith("upwind3d_tma_kernel")
     with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, (8, 8, 9)) as up:
@@ -420,6 +420,6 @@ def test_describe_names_the_kernel_and_the_reason_for_the_generic_one(gpu_fb):
     off, w = oracle.laplacian_stencil(3)
     st = {tuple(int(v) for v in o): float(c) for o, c in zip(off, w)}
     with gpu_fb.Filter((8, 16, 128), [0.0] * 3, [1.0] * 3, st) as fl:
-        assert "lap7_fused2_kernel" in fl.describe()
+        assert "lap7_fused2_lean_kernel" in fl.describe()
     with gpu_fb.Filter((8, 10, 12), [0.0] * 3, [1.0] * 3, st) as fl:
         assert "stencil_generic_kernel" in fl.describe() and "divides the plane" in fl.describe()
