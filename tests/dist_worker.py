@@ -61,6 +61,49 @@ def host_model_of_the_slab_ring(rank, world):
     assert np.array_equal(cur, ref[lo:hi]), "host slab-ring model differs from the single-domain result"
 
 
+def host_model_of_the_reversed_ring(rank, world):
+    """Negative velocity along the slab axis (capi.cu: flip[0] on several slabs, runtime.cu: Field::ring_reversed): every
+    rank holds ITS OWN global planes mirrored in place, runs the positive-velocity update on them, and the ring runs
+    backwards -- the top device plane (the lowest global plane) goes to rank-1's ghost below.  With a ghost depth of 2
+    and sweeps of two fused steps, restated with numpy slabs and gloo send/recv; must equal the single-domain result
+    for v0 < 0 bit for bit."""
+    n0, n1, n2 = 6 * world, 5, 8
+    T, steps = 2, 4 * world + 2
+    rng = np.random.default_rng(SEED + 9)
+    full = rng.random((n0, n1, n2))
+    lo, hi = fb.slab_partition(n0, world, rank)
+    nxt, prv = (rank - 1) % world, (rank + 1) % world       # reversed: my top planes go to rank - 1
+    c = -0.1                                                 # ((dt * -v) * -1) / dx == ((dt * v) * +1) / dx: same bits
+    dev = full[lo:hi][::-1].copy()                           # mirrored in place: device plane i = global plane hi-1-i
+    ghost = np.stack([full[(hi + T - 1 - g) % n0] for g in range(T)])   # device planes -T..-1 = global hi+T-1 .. hi
+
+    def update(plane, below):
+        t = plane - c * (below - plane)
+        t = t - c * (np.roll(plane, 1, axis=0) - plane)
+        t = t - c * (np.roll(plane, 1, axis=1) - plane)
+        return t
+
+    for _ in range(steps // T):
+        ext = np.concatenate([ghost, dev])
+        for _ in range(T):                                   # each fused step eats one plane at the bottom
+            ext = np.stack([update(ext[i], ext[i - 1]) for i in range(1, ext.shape[0])])
+        new = ext
+        assert new.shape[0] == dev.shape[0]
+        send = dist.isend(torch.from_numpy(new[-T:].copy()), nxt)
+        buf = torch.empty((T, n1, n2), dtype=torch.float64)
+        recv = dist.irecv(buf, prv)
+        send.wait(); recv.wait()
+        dev, ghost = new, buf.numpy().copy()
+    # single-domain result for v0 < 0: the upwind neighbour along axis 0 is i + 1 (ref: upwind.cxx:34-35,75-76)
+    ref = full.copy()
+    for _ in range(steps):
+        old = ref.copy()
+        ref = ref - c * (np.roll(old, -1, axis=0) - old)        # coeff = ((dt * -1) * +1) / dx: the same -0.1
+        ref = ref - c * (np.roll(old, 1, axis=1) - old)
+        ref = ref - c * (np.roll(old, 1, axis=2) - old)
+    assert np.array_equal(dev[::-1], ref[lo:hi]), "reversed slab ring differs from the single-domain result"
+
+
 def host_model_of_the_two_sided_ring_with_fused_pairs(rank, world):
     """The stencil engine's multi-slab protocol (runtime.cu: field_run_sweeps / sweep_device_direct, capi.cu:
     fdb_stencil_iterate) restated with numpy slabs and gloo send/recv: G = 2 ghost planes on both sides, a plan of
@@ -144,11 +187,12 @@ def cpu_main():
             assert e.code == -2
     # 3. slabs tile the axis exactly
     ranges = [None] * world
-    dist.all_gather_object(ranges, fb.slab_partition(64, world, rank))
-    assert ranges[0][0] == 0 and ranges[-1][1] == 64
+    dist.all_gather_object(ranges, fb.slab_partition(16 * world, world, rank))
+    assert ranges[0][0] == 0 and ranges[-1][1] == 16 * world
     assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
     # 4. the halo protocol itself
     host_model_of_the_slab_ring(rank, world)
+    host_model_of_the_reversed_ring(rank, world)
     host_model_of_the_two_sided_ring_with_fused_pairs(rank, world)
     dist.barrier()
     print(f"RANK {rank} OK cpu", flush=True)

@@ -1,4 +1,4 @@
-"""world_size-2 gloo runs on CPU: the host side of the N>1 path (id plumbing, slab
+"""world_size-2 (and one world_size-3) gloo runs on CPU: the host side of the N>1 path (id plumbing, slab
 partition, the halo-ring protocol modelled on the host) and bench.py's reference arm."""
 import json
 import os
@@ -21,6 +21,14 @@ def test_two_ranks_gloo_host_plumbing_and_halo_protocol(lib_built):
     p = torchrun(2, [os.path.join(ROOT, "tests", "dist_worker.py"), "cpu"], 29611)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "RANK 0 OK cpu" in p.stdout and "RANK 1 OK cpu" in p.stdout
+
+
+def test_three_ranks_gloo_ring_direction(lib_built):
+    """With two ranks the previous and the next slab are the same rank; three make the ring's direction matter (the
+    one-sided ring, the reversed ring of mirrored slabs, the two-sided ring with fused pairs)."""
+    p = torchrun(3, [os.path.join(ROOT, "tests", "dist_worker.py"), "cpu"], 29615)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert all(f"RANK {r} OK cpu" in p.stdout for r in range(3))
 
 
 def test_bench_reference_arm_under_torchrun_only_rank0_reports():
