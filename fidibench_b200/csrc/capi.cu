@@ -871,7 +871,7 @@ int fdb_stencil_describe(const fdb_stencil* h, char* text, size_t capacity) {
                     : !seven                        ? "offsets beyond the radius-1 axis-aligned (7-point) set"
                     : (f.geo.ndims == 1 || (f.geo.ndims == 2 && f.geo.n[0] != 1))
                         ? "1-D, or a 2-D problem on several slabs: the tiled kernel needs whole planes"
-                        : "no tile (8/16/32 rows x 32/64/128 cells) divides the plane";
+                        : "odd (or < 4) last extent, or a single row per plane";
   snprintf(text, capacity, "stencil_generic_kernel (one thread per cell, several times slower than the tiled kernels): %s; %d slab(s)",
            why, f.nparts);
   return FDB_OK;

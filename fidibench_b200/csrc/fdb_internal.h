@@ -112,6 +112,7 @@ struct Slab {
   CUtensorMap tm_ghi[2];   // the G planes above local plane nloc-1
   bool have_tma = false;
   int tma_cfg = 0;         // index into the TMA kernel configuration table
+  bool lap_ragged = false; // 7-point single-apply kernel: the plane is not a whole number of tiles
   // fused (temporal blocking) kernel: 8 tensor maps per buffer parity, encoded on first use
   alignas(64) unsigned char fused_maps[2][8 * sizeof(CUtensorMap)];
   int fused_T = 0;

@@ -264,7 +264,12 @@ __device__ __forceinline__ double acc_branch(double acc, double w, int /*one*/, 
 // acc = 0; for each present branch in order: acc = acc + w * in[...]   (ref: Filter.cpp:247-251)
 // The last branch (i+1) arrives one plane later, so the first six are accumulated when
 // plane i is in shared memory and the sum is finished when plane i+1 lands.
-template <class C>
+// RAGGED: the plane is not a whole number of tiles (any n1 >= 2, any even n2 >= 4).  TMA zero-fills what lies outside
+// the tensor; the periodic neighbours of the plane's last row / last cell pair then sit INSIDE the last tiles, so the
+// row below comes from the wrap row (`bot`) for whichever thread row holds global row n1-1, the cell to the right from
+// the wrap columns for whichever thread holds cells n2-2, n2-1, and stores are masked.  Planes that tile exactly keep
+// the unmasked instantiation.
+template <class C, bool RAGGED = false>
 __global__ void __launch_bounds__(C::THREADS)
     lap7_tma_kernel(const __grid_constant__ CUtensorMap tm_body, const __grid_constant__ CUtensorMap tm_row,
                     const __grid_constant__ CUtensorMap tm_col, const __grid_constant__ CUtensorMap tm_glo,
@@ -352,7 +357,10 @@ __global__ void __launch_bounds__(C::THREADS)
     const int64_t k = (int64_t)kt * C::BK + 2 * tx;
     const int64_t j = (int64_t)jt * C::BJ + r0;
     const bool wrapl_lane = (kt == 0) && (tx == 0);
-    const bool wrapr_lane = (kt == a.nkt - 1) && (tx == C::TX - 1);
+    const bool wrapr_lane = (kt == a.nkt - 1) && (k + 2 == a.n2);  // the thread that holds the plane's last two cells
+    // tile row that holds the plane's last row (the tile's last row unless the tile is ragged)
+    const int last_row = RAGGED ? (int)((a.n1 - (int64_t)jt * C::BJ < C::BJ ? a.n1 - (int64_t)jt * C::BJ : C::BJ)) - 1 : C::BJ - 1;
+    const bool k_ok = !RAGGED || k < a.n2;
 
     double2 below[C::R];    // plane i-1
     double2 partial[C::R];  // first six branches of plane i-1's output (waiting for plane i)
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(C::THREADS)
           x = acc_branch(x, a.w[6], a.one[6], above[r].x);
           y = acc_branch(y, a.w[6], a.one[6], above[r].y);
         }
-        st_global_v2(orow + (int64_t)r * a.n2, x, y);
+        if (!RAGGED || (k_ok && r0 + r <= last_row)) st_global_v2(orow + (int64_t)r * a.n2, x, y);
       }
     };
 
@@ -393,6 +401,8 @@ __global__ void __launch_bounds__(C::THREADS)
           (r0 + C::R == C::BJ) ? st + C::BOT_OFF : st + C::BODY_OFF + (r0 + C::R) * C::ROW_BYTES;
       const double2 up = lds_v2(up_row + col);
       const double2 dn = lds_v2(dn_row + col);
+      double2 bot = dn;
+      if (RAGGED) bot = lds_v2(st + C::BOT_OFF + col);  // global row 0 (periodic), wherever the plane's last row sits
 #pragma unroll
       for (int r = 0; r < C::R; ++r) {
         const uint32_t row = st + C::BODY_OFF + (r0 + r) * C::ROW_BYTES;
@@ -409,7 +419,8 @@ __global__ void __launch_bounds__(C::THREADS)
 #pragma unroll
       for (int r = 0; r < C::R; ++r) {
         const double2 jm = (r == 0) ? up : ctr[r - 1];
-        const double2 jp = (r == C::R - 1) ? dn : ctr[r + 1];
+        double2 jp = (r == C::R - 1) ? dn : ctr[r + 1];
+        if (RAGGED && r0 + r == last_row) jp = bot;
         double x = 0.0, y = 0.0;
         if (a.has[0]) { x = acc_branch(x, a.w[0], a.one[0], below[r].x); y = acc_branch(y, a.w[0], a.one[0], below[r].y); }
         if (a.has[1]) { x = acc_branch(x, a.w[1], a.one[1], jm.x); y = acc_branch(y, a.w[1], a.one[1], jm.y); }
@@ -595,18 +606,23 @@ typedef void (*Lap7Kernel)(const CUtensorMap, const CUtensorMap, const CUtensorM
 struct Lap7Config {
   int BJ, BK, BKH, threads, smem;
   Lap7Kernel kernel;
+  Lap7Kernel kernel_ragged;  // for planes the tile does not divide (null: this configuration only runs exact tilings)
   const char* name;
 };
 template <class C>
 constexpr Lap7Config make_lap_cfg(const char* name) {
-  return Lap7Config{C::BJ, C::BK, C::BKH, C::THREADS, C::SMEM_BYTES, lap7_tma_kernel<C>, name};
+  return Lap7Config{C::BJ, C::BK, C::BKH, C::THREADS, C::SMEM_BYTES, lap7_tma_kernel<C, false>, nullptr, name};
+}
+template <class C>
+constexpr Lap7Config make_lap_cfg_ragged(const char* name) {
+  return Lap7Config{C::BJ, C::BK, C::BKH, C::THREADS, C::SMEM_BYTES, lap7_tma_kernel<C, false>, lap7_tma_kernel<C, true>, name};
 }
 const Lap7Config kLapCfgs[] = {
-    make_lap_cfg<Lap7Cfg<16, 128, 4, 5>>("bj16_bk128_r4_s5"),
+    make_lap_cfg_ragged<Lap7Cfg<16, 128, 4, 5>>("bj16_bk128_r4_s5"),
     make_lap_cfg<Lap7Cfg<32, 128, 4, 3>>("bj32_bk128_r4_s3"),
     make_lap_cfg<Lap7Cfg<32, 128, 8, 3>>("bj32_bk128_r8_s3"),
-    make_lap_cfg<Lap7Cfg<16, 64, 4, 6>>("bj16_bk64_r4_s6"),
-    make_lap_cfg<Lap7Cfg<8, 32, 4, 6>>("bj8_bk32_r4_s6"),
+    make_lap_cfg_ragged<Lap7Cfg<16, 64, 4, 6>>("bj16_bk64_r4_s6"),
+    make_lap_cfg_ragged<Lap7Cfg<8, 32, 4, 6>>("bj8_bk32_r4_s6"),
     make_lap_cfg<Lap7Cfg<16, 128, 4, 6>>("bj16_bk128_r4_s6"),
     make_lap_cfg<Lap7Cfg<16, 128, 4, 8>>("bj16_bk128_r4_s8"),
     make_lap_cfg<Lap7Cfg<16, 128, 2, 6>>("bj16_bk128_r2_s6"),
@@ -626,10 +642,12 @@ int lap7_slot(const int* o) {
   return -1;
 }
 
-// the largest configured tile that divides the plane (the kernel has no ragged-tile path)
-int lap7_pick_cfg(const Field& f) {
+// the largest configured tile that divides the plane; failing that (round 2) the ragged-tile configuration that wastes
+// the fewest tile cells -- any n1 >= 2 and any even n2 >= 4.  *ragged tells which kernel instantiation runs.
+int lap7_pick_cfg(const Field& f, bool* ragged) {
   const int forced = env_int("FDB_LAP_CFG", -1);
   const int64_t n1 = f.geo.n[1], n2 = f.geo.n[2];
+  *ragged = false;
   // round-1 sweeps (profiles/r01g_lap7_cfg_sweep.txt): on 1024^2 planes the 8-rows-per-thread
   // tile (index 10) is ~6 % ahead, on 512^2 planes the default 4-rows-per-thread one
   if (forced < 0 && n1 * n2 >= 768 * 768 && n1 % kLapCfgs[10].BJ == 0 && n2 % kLapCfgs[10].BK == 0) return 10;
@@ -637,7 +655,17 @@ int lap7_pick_cfg(const Field& f) {
     if (forced >= 0 && c != forced) continue;
     if (n1 % kLapCfgs[c].BJ == 0 && n2 % kLapCfgs[c].BK == 0) return c;
   }
-  return -1;
+  if (env_int("FDB_LAP_NO_RAGGED", 0) != 0 || n1 < 2 || n2 < 4 || n2 % 2 != 0) return -1;
+  int best = -1;
+  int64_t best_cells = 0;
+  for (int c = 0; c < kNumLapCfgs; ++c) {
+    if (!kLapCfgs[c].kernel_ragged || (forced >= 0 && c != forced)) continue;
+    const int64_t bj = kLapCfgs[c].BJ, bk = kLapCfgs[c].BK;
+    const int64_t cells = ((n1 + bj - 1) / bj * bj) * ((n2 + bk - 1) / bk * bk);
+    if (best < 0 || cells < best_cells) { best = c; best_cells = cells; }
+  }
+  *ragged = best >= 0;
+  return best;
 }
 }  // namespace
 
@@ -646,9 +674,11 @@ int tma_encode_slab_lap7(Field* f, int d) {
   s.have_tma = false;
   const bool plane2d = f->geo.ndims == 2 && f->geo.n[0] == 1;
   if (f->geo.ndims != 3 && !plane2d) return FDB_OK;
-  const int c = lap7_pick_cfg(*f);
+  bool ragged = false;
+  const int c = lap7_pick_cfg(*f, &ragged);
   if (c < 0) return FDB_OK;
   s.tma_cfg = c;
+  s.lap_ragged = ragged;
   const Lap7Config& C = kLapCfgs[c];
   const int64_t n1 = f->geo.n[1], n2 = f->geo.n[2];
   FDB_CUDA(cudaSetDevice(s.device));
@@ -684,6 +714,7 @@ int stencil_lap7_prepare(const Field& f, int d) {
   KernelAttr& at = g_lap_attr[sl.device & 15][sl.tma_cfg];
   if (!at.done) {
     FDB_CUDA(cudaFuncSetAttribute(C.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
+    if (C.kernel_ragged) FDB_CUDA(cudaFuncSetAttribute(C.kernel_ragged, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
     int nb = 0;
     FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, C.kernel, C.threads, C.smem));
     cudaDeviceProp prop;
@@ -709,8 +740,8 @@ int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend
   a.nloc = sl.nloc();
   a.ibeg = ibeg;
   a.iend = iend;
-  a.njt = (int)(a.n1 / C.BJ);
-  a.nkt = (int)(a.n2 / C.BK);
+  a.njt = (int)((a.n1 + C.BJ - 1) / C.BJ);
+  a.nkt = (int)((a.n2 + C.BK - 1) / C.BK);
   a.G = f.G;
   for (int i = 0; i < 7; ++i) { a.w[i] = 0.0; a.has[i] = 0; a.one[i] = 0; }
   for (int i = 0; i < b.nbranch; ++i) {
@@ -738,8 +769,8 @@ int launch_stencil_lap7(const Field& f, int d, int X, int64_t ibeg, int64_t iend
   // FDB_MAX_CTAS (tests): fewer CTAs than the device holds, so every CTA walks many work items
   if (const int cap = env_int("FDB_MAX_CTAS", 0); cap > 0 && grid > cap) grid = cap;
   const int p = X;
-  C.kernel<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p],
-                                                     sl.tm_ghi[p], a);
+  const Lap7Kernel kern = sl.lap_ragged ? C.kernel_ragged : C.kernel;
+  kern<<<(unsigned)grid, C.threads, C.smem, s>>>(sl.tm_body[p], sl.tm_row[p], sl.tm_col[p], sl.tm_glo[p], sl.tm_ghi[p], a);
   count_launch();
   FDB_CUDA(cudaGetLastError());
   return FDB_OK;
