@@ -258,7 +258,7 @@ def test_fuse_argument_validation(gpu_fb, monkeypatch):
 
 
 @pytest.mark.parametrize("ngpus", [2, 4])
-@pytest.mark.parametrize("fuse", [2, 3])
+@pytest.mark.parametrize("fuse", [2, 3, 4])
 def test_fused_in_process_slabs(gpu_fb, ngpus, fuse):
     if gpu_fb.device_count() < ngpus:
         pytest.skip(f"needs {ngpus} GPUs")
