@@ -820,6 +820,7 @@ int field_run_sweeps(Field* f, SweepLauncher* L, const int* depths, int n) {
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) return set_error(FDB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
         if (f->plan_graphs.size() >= 16) {  // plans vary with (steps, dt): keep the cache small
+          FDB_CUDA(cudaStreamSynchronize(s.s_main));  // the evicted graph may still be running (rare path)
           cudaGraphExecDestroy(f->plan_graphs.front().exec);
           f->plan_graphs.erase(f->plan_graphs.begin());
         }
