@@ -172,3 +172,21 @@ def test_cuda_graph_replay_of_small_plans_is_bitwise_and_counts_launches(gpu_fb)
         for _ in range(11):
             r = C.stencil_apply(r, off, w)
         assert np.array_equal(fl.get(), r)
+
+
+def test_cuda_graph_cache_eviction_with_replays_still_queued(gpu_fb):
+    """More than 16 distinct plans on one small field: the graph cache drops its oldest executable graphs while earlier
+    replays are still queued on the stream (no sync between the calls).  Bit-exact after 960 time steps
+    (profiles/r02gg_graph_cache_eviction.txt)."""
+    rng = np.random.default_rng(SEED + 231)
+    a = rng.random((16, 24, 64))
+    total = 0
+    with gpu_fb.Upwind([1.0] * 3, [1.0] * 3, a.shape) as up:
+        up.set_field(a)
+        dt = up.default_dt()
+        for _ in range(2):
+            for steps in range(5, 45, 2):   # 20 plans; the field's parity differs between the two rounds for odd totals
+                up.advect_async(steps, dt)
+                total += steps
+        out = up.field()
+    assert np.array_equal(out, C.upwind_advect(a, total, dt=dt))
